@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- pooled-embedding-rows/s of the sharded-embedding hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one synthetic Criteo-1TB-shaped batch
+(BASELINE.json configs[1] at N=1: 26 sparse features, the Criteo-Terabyte table
+sizes, dim 32, batch 65 536, one id per sample per feature, Zipf(1.05) ids,
+Adagrad lr 0.01): fused lookup forward -> [B, 26*D] dense-MLP input, then the
+backward of that lookup fused with the sparse Adagrad update.  At N>1
+(configs[2], dim 64) tables larger than the batch are row-sharded over the ranks
+and go through partition -> NVSwitch push all-to-all -> owner gather -> stitch.
+`value` = B*F*N pooled rows / max-over-ranks device time of the K timed steps
+(inputs resident in HBM); `e2e` = the same with the ids coming from pinned host
+memory and the pooled output copied back to the host inside the timed region,
+through the C-ABI host entry (hbGroupLookupForwardHost).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# docs/tutorial/ranking/criteo/data/spec.json:105-355 (Criteo-Terabyte vocabularies)
+CRITEO_SIZES = [39884406, 39043, 17289, 7420, 20263, 3, 7120, 1543, 63, 38532951, 2953546,
+                403346, 10, 2208, 11938, 155, 4, 976, 14, 39979771, 25641295, 39664984,
+                585935, 12972, 108, 36]
+NUM_BATCHES = 4  # distinct pre-generated id batches the steps rotate over
+
+
+def parse_args():
+  p = argparse.ArgumentParser()
+  p.add_argument('--gpus', type=int, default=1)
+  p.add_argument('--steps', type=int, default=50)
+  p.add_argument('--warmup', type=int, default=5)
+  p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  p.add_argument('--dim', type=int, default=0, help='0: 32 at N=1, 64 at N>1')
+  p.add_argument('--batch', type=int, default=65536)
+  p.add_argument('--dist', default='zipf', choices=['zipf', 'uniform'])
+  p.add_argument('--alpha', type=float, default=1.05)
+  p.add_argument('--mode', default='train', choices=['train', 'fwd'])
+  p.add_argument('--max-rows', type=int, default=0, help='cap table rows (debug)')
+  p.add_argument('--cpu-sample-steps', type=int, default=3)
+  p.add_argument('--no-cpu-baseline', action='store_true')
+  p.add_argument('--no-e2e', action='store_true')
+  p.add_argument('--capacity-factor', type=float, default=2.0)
+  return p.parse_args()
+
+
+def table_sizes(args):
+  s = list(CRITEO_SIZES)
+  if args.max_rows:
+    s = [min(n, args.max_rows) for n in s]
+  return s
+
+
+def gen_ids_numpy(rng, n, vocab, dist, alpha):
+  """Bounded power-law ranks by inverse CDF, scrambled over the vocabulary."""
+  if dist == 'uniform' or vocab <= 2:
+    return rng.randint(0, vocab, n).astype(np.int64)
+  u = rng.random_sample(n)
+  a = 1.0 - alpha
+  rank = np.floor(((vocab ** a - 1.0) * u + 1.0) ** (1.0 / a)).astype(np.int64)
+  rank = np.clip(rank, 1, vocab) - 1
+  return (rank * 2654435761) % vocab
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+       'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.index, self.proc, self.lines = index, None, []
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+           '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.t = threading.Thread(target=self._read, daemon=True)
+      self.t.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    time.sleep(0.15)
+    self.proc.terminate()
+    self.t.join(timeout=2)
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for l in self.lines:
+      f = [x.strip() for x in l.split(',')]
+      if len(f) < 9:
+        continue
+      try:
+        sm.append(float(f[1])); mx.append(float(f[2]))
+      except ValueError:
+        continue
+      for nme, v in zip(names, f[5:9]):
+        if v.lower().startswith('active'):
+          reasons.add(nme)
+    return {'sm_mhz': float(np.median(sm)) if sm else None,
+            'sm_max_mhz': max(mx) if mx else None, 'samples': len(sm),
+            'reasons': sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------
+# CPU arm: the oracle (reference-semantics restatement) on the host cores
+# --------------------------------------------------------------------------------
+def cpu_arm(args, sizes, dim, steps, warmup, rank0_only_note=''):
+  """Times oracle/ (TF-1.15 embedding_lookup_sparse: unique->gather->segment
+  reduce; then dedup + SparseApplyAdagrad) on the host cores; features in
+  parallel threads (ctypes releases the GIL).  Returns (rows_per_s, info)."""
+  from concurrent.futures import ThreadPoolExecutor
+  import psutil
+  from oracle import hb_oracle as o
+  o.lib()
+  F, B = len(sizes), args.batch
+  cores = os.cpu_count() or 1
+  avail = psutil.virtual_memory().available
+  need = sum(sizes) * dim * 4 * (2 if args.mode == 'train' else 1)
+  scale = 1.0
+  if need > 0.6 * avail:
+    scale = 0.6 * avail / need
+  csizes = [max(1, int(n * scale)) for n in sizes]
+  rng = np.random.RandomState(1234)
+  tables = [np.zeros((n, dim), np.float32) for n in csizes]       # lazily paged
+  accs = [np.zeros((n, dim), np.float32) for n in csizes] if args.mode == 'train' else None
+  nb = min(NUM_BATCHES, 2)
+  batches = [[gen_ids_numpy(rng, B, n, args.dist, args.alpha) for n in csizes] for _ in range(nb)]
+  offsets = np.arange(B + 1, dtype=np.int64)
+  grad = rng.randn(B, F * dim).astype(np.float32)
+  out = np.empty((B, F * dim), np.float32)
+  for k in range(F):  # touch the rows the batches use so page faults are not timed
+    for b in batches:
+      u = np.unique(b[k])
+      tables[k][u] = 1e-3
+      if accs is not None:
+        accs[k][u] = 0.1
+
+  def one_feature(k, ids):
+    o.embedding_lookup_sparse(tables[k], ids, offsets, 'mean', out=out[:, k * dim:(k + 1) * dim])
+    if accs is not None:
+      rg = o.lookup_row_grads(grad[:, k * dim:(k + 1) * dim], offsets, 'mean')
+      o.sparse_apply_adagrad(tables[k], accs[k], ids, rg, 0.01)
+
+  workers = min(cores, F)
+  with ThreadPoolExecutor(workers) as ex:
+    def step(i):
+      b = batches[i % nb]
+      list(ex.map(lambda k: one_feature(k, b[k]), range(F)))
+    for i in range(warmup):
+      step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+      step(i)
+    dt = time.perf_counter() - t0
+  value = B * F * steps / dt
+  info = {'value': value, 'unit': 'pooled-embedding-rows/s', 'cores': workers,
+          'host_cores': cores,
+          'kind': 'port',
+          'sample': (f'{steps} steps x (26 feats x {B} ids) of the same workload, '
+                     f'{"fwd+bwd+Adagrad" if args.mode == "train" else "fwd"}, tables '
+                     f'{"full size" if scale == 1.0 else f"scaled x{scale:.2f} to fit host RAM"}, '
+                     f'{workers} threads (one per feature); oracle/hb_oracle.c port of the '
+                     'TF-1.15 CPU semantics (the tf115 wheel cannot run here)' + rank0_only_note),
+          'ms_per_step': dt / steps * 1e3}
+  return value, info
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  dim = args.dim or (32 if args.gpus == 1 else 64)
+  sizes = table_sizes(args)
+  steps = max(1, min(args.steps, 5))
+  warmup = max(1, min(args.warmup, 2))
+  value, info = cpu_arm(args, sizes, dim, steps, warmup)
+  line = {
+      'impl': 'reference', 'metric': 'pooled-embedding-rows/sec', 'value': value,
+      'unit': 'pooled-embedding-rows/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
+      'ms_per_step': info['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': workload_config(args, dim, sizes),
+      'cpu_baseline': info,
+      'e2e': {'value': value, 'unit': 'pooled-embedding-rows/s', 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+      'note': ('reference arm = CPU restatement of the reference path (oracle port; TF-1.15 '
+               'cannot be installed here), bounded to %d steps' % steps)}
+  print(json.dumps(line))
+
+
+def workload_config(args, dim, sizes):
+  return {'workload': ('criteo-1tb-synthetic: 26 sparse feats, table sizes %d..%d rows, dim %d, '
+                       'batch %d per rank, 1 id/sample/feature, %s ids, %s' %
+                       (min(sizes), max(sizes), dim, args.batch,
+                        f'zipf({args.alpha})' if args.dist == 'zipf' else 'uniform',
+                        'fwd + bwd + sparse Adagrad(lr=0.01)' if args.mode == 'train' else 'fwd only')),
+          'global_batch': args.batch * args.gpus, 'features': len(sizes), 'dim': dim,
+          'parallelism': 'single-gpu' if args.gpus == 1 else f'row-sharded tables x{args.gpus} (id % W), data-parallel batch',
+          'cache': ('inputs larger than L2: %.1f GB of tables, steps rotate over %d id batches' %
+                    (sum(sizes) * dim * 4 / 1e9, NUM_BATCHES))}
+
+
+# --------------------------------------------------------------------------------
+def run_ours(args):
+  import torch
+  import torch.distributed as dist
+  import hybridbackend_b200 as hb
+  from hybridbackend_b200 import _lib
+  L = _lib.lib()
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if world != args.gpus:
+    if world == 1 and args.gpus > 1:
+      raise SystemExit('launch N>1 with torch.distributed.run (one rank per GPU)')
+  torch.cuda.set_device(local_rank)
+  dev = torch.device(f'cuda:{local_rank}')
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  dim = args.dim or (32 if world == 1 else 64)
+  sizes = table_sizes(args)
+  F, B = len(sizes), args.batch
+
+  # ---- tables (row-sharded where the reference shards them) ----------------------
+  coll = None
+  if world > 1:
+    from hybridbackend_b200.embedding.sharded import plan_window_bytes
+    sharded_dims = [dim for n in sizes if not hb.embedding.is_small_table(n, world, B)]
+    wbytes = plan_window_bytes(world, [B] * len(sharded_dims), sharded_dims, args.capacity_factor)
+    coll = hb.distribute.Collective(rank, world, window_bytes=wbytes, device=dev)
+  g = torch.Generator(device=dev).manual_seed(1234 + rank)
+  tables = []
+  for k, n in enumerate(sizes):
+    t = hb.embedding.ShardedEmbeddingWeights(f'emb{k}', n, dim, rank, world, batch_size=B, device=dev)
+    t.weight.uniform_(-1e-3, 1e-3, generator=g)
+    tables.append(t)
+  gl = hb.embedding.GroupLookup(tables, ['mean'] * F, collective=coll, max_nnz=[B] * F,
+                                capacity_factor=args.capacity_factor)
+  opt = hb.training.Adagrad(0.01)
+
+  # ---- inputs: NUM_BATCHES id batches, device + pinned host copies ---------------
+  rng = np.random.RandomState(1234 + rank)
+  h_batches = []
+  for _ in range(NUM_BATCHES):
+    blk = np.stack([gen_ids_numpy(rng, B, n, args.dist, args.alpha) for n in sizes])  # [F, B]
+    h_batches.append(torch.from_numpy(blk).pin_memory())
+  d_batches = [hb_.to(dev) for hb_ in h_batches]
+  grad = torch.randn(B, F * dim, device=dev, generator=g)
+  out = torch.empty(B, F * dim, device=dev)
+  h_out = torch.empty(B, F * dim).pin_memory()
+  d_stage = torch.empty(F, B, dtype=torch.int64, device=dev)
+  uniq_rows = [sum(int(torch.unique(db[k]).numel()) for db in d_batches) / NUM_BATCHES for k in range(F)]
+
+  def step(i, host=False):
+    if host:
+      gl.forward_host(h_batches[i % NUM_BATCHES], d_stage, out, h_out)
+    else:
+      db = d_batches[i % NUM_BATCHES]
+      gl.forward([db[k] for k in range(F)], out=out)
+    if args.mode == 'train':
+      gl.backward_update(grad, opt)
+
+  def timed(steps, host=False):
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+      step(i, host)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+      t = torch.tensor([ms], device=dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t.item())
+      dist.barrier()
+    return ms
+
+  W_, K = max(args.warmup, 3), args.steps
+  for i in range(W_):
+    step(i)
+  hb._util.check_status(dev)
+  clocks = ClockSampler(local_rank)
+  clocks.start()
+  l0 = L.hbGetLaunchCount()
+  ms = timed(K)
+  launches = L.hbGetLaunchCount() - l0
+  clk = clocks.stop()
+  hb._util.check_status(dev)
+  value = B * F * world * K / (ms * 1e-3)
+
+  # ---- per-kernel CUDA-event pass (same K steps) for the roofline ----------------
+  L.hbProfileReset(); L.hbProfileEnable(1)
+  timed(K)
+  L.hbProfileEnable(0)
+  kern = {}
+  import ctypes as C
+  for kid in range(1, 24):
+    tms, n = C.c_double(0), C.c_int64(0)
+    L.hbProfileGet(kid, C.byref(tms), C.byref(n))
+    if n.value:
+      kern[L.hbKernelName(kid).decode()] = {'ms_total': tms.value, 'launches': n.value,
+                                            'ms_avg': tms.value / n.value}
+  L.hbProfileReset()
+  peaks = {}
+  try:
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+  except (OSError, ValueError):
+    pass
+  peak = float(peaks.get('hbm_gbs', 6650.0))
+  peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
+  local_feats = [k for k in range(F) if k in gl.local_idx]
+  alg = {}
+  # forward gather+pool: per pooled row L*(8+4D) read + 4D written, L=1
+  alg['lookup_fwd'] = len(local_feats) * B * (8 + 4 * dim + 4 * dim)
+  # update: per id 8 B (sorted row+bag) + 4D grad; per unique row 4*4D (w, acc read+write)
+  alg['sparse_update'] = sum(B * (8 + 4 * dim) + uniq_rows[k] * 16 * dim for k in local_feats)
+  traffic = {}
+  try:
+    traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+  except (OSError, ValueError):
+    pass
+  roofs = []
+  for name, a in alg.items():
+    if name in kern and a > 0:
+      ach = a / (kern[name]['ms_avg'] * 1e-3) / 1e9
+      roofs.append({'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                    'frac': ach / peak, 'traffic': traffic.get(name), 'alg_bytes_per_launch': a,
+                    'ms_avg': kern[name]['ms_avg'], 'peak_source': peak_src})
+  roofs.sort(key=lambda r: -r['ms_avg'])
+  roofline = roofs[0] if roofs else None
+
+  # ---- end-to-end through the host-buffer C-ABI entry ------------------------------
+  e2e = None
+  if not args.no_e2e and world == 1:
+    for i in range(2):
+      step(i, host=True)
+    ms_e = timed(K, host=True)
+    e2e = {'value': B * F * world * K / (ms_e * 1e-3), 'unit': 'pooled-embedding-rows/s',
+           'h2d_bytes_per_step': F * B * 8, 'd2h_bytes_per_step': B * F * dim * 4,
+           'ms_per_step': ms_e / K,
+           'note': 'ids from pinned host memory, pooled [B, F*D] output copied back to pinned host; '
+                   'upstream gradient stays on the device (it comes from the dense MLP)'}
+  elif not args.no_e2e:
+    for i in range(2):
+      step(i, host=True)
+    ms_e = timed(K, host=True)
+    e2e = {'value': B * F * world * K / (ms_e * 1e-3), 'unit': 'pooled-embedding-rows/s',
+           'h2d_bytes_per_step': F * B * 8, 'd2h_bytes_per_step': B * F * dim * 4,
+           'ms_per_step': ms_e / K}
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    _, cpu = cpu_arm(args, sizes, dim, args.cpu_sample_steps, 1)
+
+  if rank == 0:
+    line = {
+        'metric': 'pooled-embedding-rows/sec', 'value': value, 'unit': 'pooled-embedding-rows/s',
+        'n_gpus': world, 'steps': K, 'warmup': W_, 'ms_per_step': ms / K, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, dim, sizes), 'clocks': clk, 'e2e': e2e,
+        'gpu_launches': int(launches), 'roofline': roofline, 'roofline_all': roofs,
+        'kernels': kern, 'cpu_baseline': cpu,
+        'roofline_note': 'per-kernel CUDA events recorded by the library on the launching stream in '
+                         'a second pass of the same K steps (hbProfileEnable)',
+        'hbm_roofline_rows_per_s_per_gpu': peak * 1e9 / (8 + 8 * dim) if args.mode == 'fwd' else
+                                           peak * 1e9 / ((8 + 8 * dim) + (8 + 20 * dim)),
+    }
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  args = parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_ours(args)
+
+
+if __name__ == '__main__':
+  main()

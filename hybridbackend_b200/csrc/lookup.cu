@@ -1,0 +1,297 @@
+// lookup.cu -- K3: fused multi-table gather + segment pooling (forward).
+//
+// One launch covers every feature of the group.  A feature with row width
+// dim = 4*G*V floats is served by sub-warp groups of G lanes (G a power of two
+// <= 32), each lane owning V float4 columns of the row, so a warp issues
+// 128-bit loads that cover whole rows (D=32: 4 rows per warp instruction, each
+// row one full 128-byte line).  Accumulation is in registers, fp32, in bag
+// order -- the order TF-1.15's SparseSegment* CPU kernel uses -- so results are
+// bit-identical to the oracle (oracle/hb_oracle.c: hbo_embedding_lookup_sparse).
+// Memory-level parallelism: every group keeps kBagsPerGroup independent bags
+// (one-id-per-bag fast path) or 4 ids of one bag in flight.
+//
+// HBM traffic per pooled row (algorithmic): L*(8 + 4*dim) read + 4*dim written.
+#include "common.cuh"
+
+namespace hb {
+
+constexpr int kLookupThreads = 256;
+constexpr int kBagsPerGroup = 4;
+constexpr int kMaxLookupFeats = 128;
+
+struct LookupFeat {
+  const float* table;
+  const int64_t* ids;
+  const int64_t* offsets;
+  float* out;
+  int64_t rows;
+  int64_t out_stride;
+  int64_t id_div;
+  int32_t nbags;
+  int32_t dim;
+  int32_t combiner;
+  int32_t div_shift;  // log2(id_div) or -1
+  int32_t cta_begin;
+  int32_t log2g;
+};
+
+struct LookupParams {
+  LookupFeat f[kMaxLookupFeats];
+  int32_t* status;
+  int32_t nfeats;
+  int32_t total_ctas;
+};
+
+__device__ __forceinline__ int find_feat(const LookupParams& P, int cta) {
+  int lo = 0, hi = P.nfeats - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (P.f[mid].cta_begin <= cta) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ int64_t local_row(int64_t id, const LookupFeat& F) {
+  if (id < 0) return -1;  // never a valid row
+  if (F.div_shift >= 0) return (int64_t)((uint64_t)id >> F.div_shift);
+  return id / F.id_div;
+}
+
+__device__ __forceinline__ float4 f4_add(const float4& a, const float4& b) {
+  return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z),
+                     __fadd_rn(a.w, b.w));
+}
+__device__ __forceinline__ float4 f4_div(const float4& a, float c) {
+  return make_float4(__fdiv_rn(a.x, c), __fdiv_rn(a.y, c), __fdiv_rn(a.z, c), __fdiv_rn(a.w, c));
+}
+
+template <int V>
+__global__ void __launch_bounds__(kLookupThreads)
+lookup_fwd_kernel(const __grid_constant__ LookupParams P) {
+  const int fi = find_feat(P, blockIdx.x);
+  const LookupFeat& F = P.f[fi];
+  const int chunk = blockIdx.x - F.cta_begin;
+  const int log2g = F.log2g;
+  const int groups = kLookupThreads >> log2g;
+  const int g = threadIdx.x >> log2g;
+  const int l = threadIdx.x & ((1 << log2g) - 1);
+  const int dim = F.dim;
+  const int nbags = F.nbags;
+  const int bag0 = chunk * groups * kBagsPerGroup;
+  bool oob = false;
+  bool bad_off = false;
+
+  // column c of lane l, vector v:  (v * G + l) * 4
+  int col[V];
+  bool act[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    col[v] = ((v << log2g) + l) * 4;
+    act[v] = col[v] < dim;
+  }
+
+  if (F.offsets == nullptr) {
+    // ---- one id per bag: pure gather, kBagsPerGroup rows in flight ----------
+    int64_t r[kBagsPerGroup];
+    bool ok[kBagsPerGroup];
+#pragma unroll
+    for (int u = 0; u < kBagsPerGroup; ++u) {
+      const int b = bag0 + u * groups + g;
+      ok[u] = b < nbags;
+      const int64_t id = ok[u] ? ld_nc_i64(F.ids + b) : 0;
+      r[u] = local_row(id, F);
+      if (ok[u] && (uint64_t)r[u] >= (uint64_t)F.rows) { oob = true; r[u] = -1; }
+    }
+    float4 val[kBagsPerGroup][V];
+#pragma unroll
+    for (int u = 0; u < kBagsPerGroup; ++u)
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[u] && r[u] >= 0 && act[v])
+          val[u][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.table + r[u] * dim + col[v]));
+      }
+#pragma unroll
+    for (int u = 0; u < kBagsPerGroup; ++u) {
+      const int b = bag0 + u * groups + g;
+      if (!ok[u]) continue;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (act[v])
+          *reinterpret_cast<float4*>(F.out + (int64_t)b * F.out_stride + col[v]) = val[u][v];
+    }
+  } else {
+    // ---- CSR bags: sequential fp32 accumulation in bag order ----------------
+#pragma unroll 1
+    for (int u = 0; u < kBagsPerGroup; ++u) {
+      const int b = bag0 + u * groups + g;
+      if (b >= nbags) break;
+      int64_t s = F.offsets[b];
+      int64_t e = F.offsets[b + 1];
+      if (e < s || s < 0) { bad_off = true; e = s; }
+      float4 acc[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t p = s; p < e; p += 4) {
+        int64_t r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          r[k] = -1;
+          if (p + k < e) {
+            r[k] = local_row(ld_nc_i64(F.ids + p + k), F);
+            if ((uint64_t)r[k] >= (uint64_t)F.rows) { oob = true; r[k] = -1; }
+          }
+        }
+        float4 x[4][V];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            x[k][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r[k] >= 0 && act[v])
+              x[k][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.table + r[k] * dim + col[v]));
+          }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (p + k < e)
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = f4_add(acc[v], x[k][v]);
+      }
+      const int64_t cnt = e - s;
+      if (cnt > 0 && F.combiner != HB_SUM) {
+        const float c = (F.combiner == HB_MEAN) ? (float)cnt : __fsqrt_rn((float)cnt);
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = f4_div(acc[v], c);
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (act[v])
+          *reinterpret_cast<float4*>(F.out + (int64_t)b * F.out_stride + col[v]) = acc[v];
+    }
+  }
+  if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
+  if (bad_off) raise_status(P.status, HB_STATUS_BAD_OFFSETS);
+}
+
+static int ilog2_ceil(int x) {
+  int l = 0;
+  while ((1 << l) < x) ++l;
+  return l;
+}
+
+// Shape of the work decomposition for one feature: G lanes/row, V vectors/lane.
+static void lookup_shape(int dim, int* log2g, int* v) {
+  const int vecs = dim / 4;
+  if (vecs <= 32) { *log2g = ilog2_ceil(vecs); *v = 1; return; }
+  *log2g = 5;
+  int vv = (vecs + 31) / 32;
+  int p = 1;
+  while (p < vv) p <<= 1;
+  *v = p;
+}
+
+template <int V>
+static int launch_lookup(const LookupParams& P, cudaStream_t stream) {
+  if (P.total_ctas == 0) return HB_OK;
+  {
+    KernelScope ks(HB_K_LOOKUP_FWD, stream);
+    lookup_fwd_kernel<V><<<P.total_ctas, kLookupThreads, 0, stream>>>(P);
+  }
+  HB_CUDA_OK(cudaGetLastError());
+  return HB_OK;
+}
+
+static int validate_feature(int k, const hbLookupFeature& f) {
+  HB_REQUIRE(f.dim >= 4 && f.dim % 4 == 0 && f.dim <= 1024,
+             "lookup: feature %d dim %d must be a multiple of 4 in [4,1024]", k, f.dim);
+  HB_REQUIRE(f.nbags >= 0 && f.nbags <= INT32_MAX, "lookup: feature %d bad nbags", k);
+  HB_REQUIRE(f.rows >= 0, "lookup: feature %d negative rows", k);
+  HB_REQUIRE(f.id_div >= 1, "lookup: feature %d id_div must be >= 1", k);
+  HB_REQUIRE(f.out_stride >= f.dim && f.out_stride % 4 == 0,
+             "lookup: feature %d out_stride %lld must be a multiple of 4 and >= dim", k,
+             (long long)f.out_stride);
+  HB_REQUIRE(f.combiner >= HB_SUM && f.combiner <= HB_SQRTN, "lookup: feature %d bad combiner", k);
+  if (f.nbags > 0) {
+    HB_REQUIRE(f.table && f.ids && f.out, "lookup: feature %d null pointer", k);
+    HB_REQUIRE(((uintptr_t)f.table & 15) == 0 && ((uintptr_t)f.out & 15) == 0,
+               "lookup: feature %d table/out must be 16-byte aligned", k);
+  }
+  return HB_OK;
+}
+
+}  // namespace hb
+
+extern "C" int hbGroupLookupForward(int n, const hbLookupFeature* feats, int32_t* d_status,
+                                    hbStream stream_) {
+  using namespace hb;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  HB_REQUIRE(n >= 1 && feats != nullptr, "hbGroupLookupForward: need n >= 1 features");
+  for (int k = 0; k < n; ++k) {
+    int rc = validate_feature(k, feats[k]);
+    if (rc != HB_OK) return rc;
+  }
+  // one launch per distinct V (1 for every dim <= 128), chunks of kMaxLookupFeats
+  for (int V = 1; V <= 8; V <<= 1) {
+    LookupParams P;
+    P.status = d_status;
+    P.nfeats = 0;
+    P.total_ctas = 0;
+    auto flush = [&]() -> int {
+      int rc = HB_OK;
+      if (P.nfeats > 0) {
+        switch (V) {
+          case 1: rc = launch_lookup<1>(P, stream); break;
+          case 2: rc = launch_lookup<2>(P, stream); break;
+          case 4: rc = launch_lookup<4>(P, stream); break;
+          default: rc = launch_lookup<8>(P, stream); break;
+        }
+      }
+      P.nfeats = 0;
+      P.total_ctas = 0;
+      return rc;
+    };
+    for (int k = 0; k < n; ++k) {
+      const hbLookupFeature& f = feats[k];
+      int log2g, v;
+      lookup_shape(f.dim, &log2g, &v);
+      if (v != V || f.nbags == 0) continue;
+      LookupFeat& F = P.f[P.nfeats];
+      F.table = f.table; F.ids = f.ids; F.offsets = f.offsets; F.out = f.out;
+      F.rows = f.rows; F.out_stride = f.out_stride; F.id_div = f.id_div;
+      F.nbags = (int32_t)f.nbags; F.dim = f.dim; F.combiner = f.combiner;
+      F.div_shift = ((f.id_div & (f.id_div - 1)) == 0) ? ilog2_ceil((int)f.id_div) : -1;
+      if (f.id_div > (1 << 30)) F.div_shift = -1;
+      F.cta_begin = P.total_ctas;
+      F.log2g = log2g;
+      const int groups = kLookupThreads >> log2g;
+      const int per_cta = groups * kBagsPerGroup;
+      P.total_ctas += (int)((f.nbags + per_cta - 1) / per_cta);
+      P.nfeats++;
+      if (P.nfeats == kMaxLookupFeats) {
+        int rc = flush();
+        if (rc != HB_OK) return rc;
+      }
+    }
+    int rc = flush();
+    if (rc != HB_OK) return rc;
+  }
+  return HB_OK;
+}
+
+extern "C" int hbGroupLookupForwardHost(int n, const hbLookupFeature* feats, const void* h_in_block,
+                                        void* d_in_block, size_t in_block_bytes,
+                                        const void* d_out_block, void* h_out_block,
+                                        size_t out_block_bytes, int32_t* d_status,
+                                        hbStream stream_) {
+  using namespace hb;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  HB_REQUIRE(in_block_bytes == 0 || (h_in_block && d_in_block), "hbGroupLookupForwardHost: null input block");
+  HB_REQUIRE(out_block_bytes == 0 || (h_out_block && d_out_block), "hbGroupLookupForwardHost: null output block");
+  if (in_block_bytes > 0)
+    HB_CUDA_OK(cudaMemcpyAsync(d_in_block, h_in_block, in_block_bytes, cudaMemcpyHostToDevice, stream));
+  int rc = hbGroupLookupForward(n, feats, d_status, stream_);
+  if (rc != HB_OK) return rc;
+  if (out_block_bytes > 0)
+    HB_CUDA_OK(cudaMemcpyAsync(h_out_block, d_out_block, out_block_bytes, cudaMemcpyDeviceToHost, stream));
+  return HB_OK;
+}

@@ -1,0 +1,684 @@
+// sparse_update.cu -- K5: backward of the pooled lookup fused with the sparse
+// optimizer apply (Adagrad / LazyAdam / SGD), deterministic, no float atomics.
+//
+// Pipeline (all features of the group per launch):
+//   1. bag_of_position : CSR features only -- bag index of every id position.
+//   2. LSD radix sort  : (local row, bag) pairs grouped by row, 9-bit digits,
+//                        stable, so entries of a row stay in position order
+//                        (bucket.cuh; 1..4 passes depending on the table size).
+//   3. update kernel   : a sub-warp group of G lanes walks a tile of C sorted
+//                        entries; gradient rows of a run (same row id) are summed
+//                        in registers in position order and the optimizer is
+//                        applied once per unique row (one read-modify-write of
+//                        the table row and its slot rows).  Runs that cross tile
+//                        borders are combined in shared memory inside the CTA
+//                        ("super-tile"), in tile order.
+//   4. fix-up kernel   : rows that span super-tiles (hot keys) are finished by
+//                        chaining the per-super-tile partial sums, in order.
+// Summation order is a fixed function of the input => bit-reproducible.
+//
+// Algorithmic HBM bytes per looked-up id without duplicates (Adagrad, fp32):
+//   8 (id) + 4*dim (grad) + 2*4*dim (w, acc read) + 2*4*dim (w, acc write).
+#include "bucket.cuh"
+
+namespace hb {
+
+constexpr int kUpdThreads = 256;
+constexpr int kMaxUpdFeats = 96;
+
+enum { kFirstOpen = 1, kBoth = 2, kLastOpen = 4 };
+
+struct UpdFeat {
+  float* table;
+  float* slot0;
+  float* slot1;
+  const float* grad;
+  const int64_t* offsets;   // bag sizes for mean/sqrtn (nullptr: one id per bag)
+  const uint32_t* keys;     // sorted local rows
+  const int32_t* bags;      // bag index of each sorted entry
+  float* st_part;           // [nst][2][dim] partial sums of open runs
+  uint32_t* st_key;         // [nst][2]
+  int32_t* st_flag;         // [nst]
+  int64_t rows;
+  int64_t grad_stride;
+  int32_t n;
+  int32_t dim;
+  int32_t combiner;
+  int32_t log2g;
+  int32_t cta_begin;        // first super-tile (== CTA) of this feature
+  int32_t nst;              // number of super-tiles
+};
+
+struct UpdParams {
+  UpdFeat f[kMaxUpdFeats];
+  int32_t* status;
+  int32_t nfeats;
+  int32_t total_ctas;
+  int32_t opt;
+  float lr;        // Adagrad/SGD: lr ; LazyAdam: bias-corrected lr_t
+  float beta1, beta2, eps;
+  float omb1, omb2;
+};
+
+__device__ __forceinline__ int find_upd_feat(const UpdParams& P, int cta) {
+  int lo = 0, hi = P.nfeats - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (P.f[mid].cta_begin <= cta) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4_add_rn(const float4& a, const float4& b) {
+  return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z),
+                     __fadd_rn(a.w, b.w));
+}
+
+// One optimizer step on 4 consecutive elements of a row.
+__device__ __forceinline__ void opt_apply4(const UpdParams& P, float* w, float* s0, float* s1,
+                                           const float4& g) {
+  float4 wv = *reinterpret_cast<float4*>(w);
+  const float gg[4] = {g.x, g.y, g.z, g.w};
+  float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+  if (P.opt == HB_OPT_ADAGRAD) {
+    // SparseApplyAdagrad: accum += g*g ; var -= lr*g/sqrt(accum)
+    float4 av = *reinterpret_cast<float4*>(s0);
+    float aa[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      aa[i] = __fadd_rn(aa[i], __fmul_rn(gg[i], gg[i]));
+      ww[i] = __fsub_rn(ww[i], __fdiv_rn(__fmul_rn(P.lr, gg[i]), __fsqrt_rn(aa[i])));
+    }
+    *reinterpret_cast<float4*>(s0) = make_float4(aa[0], aa[1], aa[2], aa[3]);
+  } else if (P.opt == HB_OPT_LAZY_ADAM) {
+    // LazyAdam: m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; var -= lr_t*m/(sqrt(v)+eps)
+    float4 mv = *reinterpret_cast<float4*>(s0);
+    float4 vv = *reinterpret_cast<float4*>(s1);
+    float mm[4] = {mv.x, mv.y, mv.z, mv.w};
+    float v2[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mm[i] = __fadd_rn(__fmul_rn(P.beta1, mm[i]), __fmul_rn(P.omb1, gg[i]));
+      v2[i] = __fadd_rn(__fmul_rn(P.beta2, v2[i]), __fmul_rn(P.omb2, __fmul_rn(gg[i], gg[i])));
+      ww[i] = __fsub_rn(ww[i], __fdiv_rn(__fmul_rn(P.lr, mm[i]),
+                                         __fadd_rn(__fsqrt_rn(v2[i]), P.eps)));
+    }
+    *reinterpret_cast<float4*>(s0) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(s1) = make_float4(v2[0], v2[1], v2[2], v2[3]);
+  } else {  // SGD
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ww[i] = __fsub_rn(ww[i], __fmul_rn(P.lr, gg[i]));
+  }
+  *reinterpret_cast<float4*>(w) = make_float4(ww[0], ww[1], ww[2], ww[3]);
+}
+
+template <int V>
+__device__ __forceinline__ bool apply_row(const UpdParams& P, const UpdFeat& F, uint32_t key,
+                                          const float4 (&acc)[V], const int (&col)[V],
+                                          const bool (&act)[V]) {
+  if ((uint64_t)key >= (uint64_t)F.rows) return false;  // out-of-range id (sentinel)
+  const int64_t base = (int64_t)key * F.dim;
+#pragma unroll
+  for (int v = 0; v < V; ++v)
+    if (act[v])
+      opt_apply4(P, F.table + base + col[v], F.slot0 ? F.slot0 + base + col[v] : nullptr,
+                 F.slot1 ? F.slot1 + base + col[v] : nullptr, acc[v]);
+  return true;
+}
+
+// smem per CTA: groups * (2*V*G float4 partials + 2 keys + 1 flag)
+template <int V, int C>
+__global__ void __launch_bounds__(kUpdThreads)
+sparse_update_kernel(const __grid_constant__ UpdParams P) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int fi = find_upd_feat(P, blockIdx.x);
+  const UpdFeat& F = P.f[fi];
+  const int st = blockIdx.x - F.cta_begin;
+  const int log2g = F.log2g;
+  const int G = 1 << log2g;
+  const int groups = kUpdThreads >> log2g;
+  const int g = threadIdx.x >> log2g;
+  const int l = threadIdx.x & (G - 1);
+  const int dim = F.dim;
+  const int n = F.n;
+  // smem carve-up
+  float4* s_part = reinterpret_cast<float4*>(s_raw);                  // [groups][2][V][G]
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(s_part + (size_t)groups * 2 * V * G);  // [groups][2]
+  int32_t* s_flag = reinterpret_cast<int32_t*>(s_key + groups * 2);   // [groups]
+
+  int col[V];
+  bool act[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    col[v] = ((v << log2g) + l) * 4;
+    act[v] = col[v] < dim;
+  }
+  bool oob = false;
+
+  const int64_t e0 = ((int64_t)st * groups + g) * C;
+  const int cnt = (int)max((int64_t)0, min((int64_t)C, (int64_t)n - e0));
+  int flag = 0;
+
+  if (cnt > 0) {
+    uint32_t k[C];
+    int32_t b[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      k[j] = 0xFFFFFFFFu;
+      b[j] = 0;
+      if (j < cnt) { k[j] = F.keys[e0 + j]; b[j] = F.bags[e0 + j]; }
+    }
+    const bool has_prev = e0 > 0;
+    const bool has_next = e0 + cnt < n;
+    const uint32_t pk = has_prev ? F.keys[e0 - 1] : 0u;
+    const uint32_t nk = has_next ? F.keys[e0 + cnt] : 0u;
+    // bag scale (mean: 1/count, sqrtn: 1/sqrt(count)) -- division as the oracle
+    float sc[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      sc[j] = 1.0f;
+      if (j < cnt && F.offsets != nullptr && F.combiner != HB_SUM) {
+        const int64_t c = F.offsets[b[j] + 1] - F.offsets[b[j]];
+        sc[j] = (F.combiner == HB_MEAN) ? (float)c : __fsqrt_rn((float)c);
+      }
+    }
+    float4 gv[C][V];
+#pragma unroll
+    for (int j = 0; j < C; ++j)
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        gv[j][v] = f4_zero();
+        if (j < cnt && act[v])
+          gv[j][v] = ld_nc_f4(reinterpret_cast<const float4*>(
+              F.grad + (int64_t)b[j] * F.grad_stride + col[v]));
+      }
+    if (F.combiner != HB_SUM && F.offsets != nullptr) {
+#pragma unroll
+      for (int j = 0; j < C; ++j)
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          gv[j][v] = make_float4(__fdiv_rn(gv[j][v].x, sc[j]), __fdiv_rn(gv[j][v].y, sc[j]),
+                                 __fdiv_rn(gv[j][v].z, sc[j]), __fdiv_rn(gv[j][v].w, sc[j]));
+    }
+
+    // walk the tile run by run
+    float4 acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = f4_zero();
+    uint32_t run_key = k[0];
+    bool open_left = has_prev && pk == k[0];
+    float4* my_part = s_part + (size_t)g * 2 * V * G;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      if (j < cnt) {
+        if (j > 0 && k[j] != run_key) {
+          // run [.., j) closed on the right
+          if (!open_left) {
+            if (!apply_row<V>(P, F, run_key, acc, col, act)) oob = true;
+          } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) my_part[(0 * V + v) * G + l] = acc[v];
+            if (l == 0) s_key[g * 2 + 0] = run_key;
+            flag |= kFirstOpen;
+          }
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = f4_zero();
+          run_key = k[j];
+          open_left = false;
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = f4_add_rn(acc[v], gv[j][v]);
+      }
+    }
+    const bool open_right = has_next && nk == run_key;
+    if (!open_left && !open_right) {
+      if (!apply_row<V>(P, F, run_key, acc, col, act)) oob = true;
+    } else if (open_left) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) my_part[(0 * V + v) * G + l] = acc[v];
+      if (l == 0) s_key[g * 2 + 0] = run_key;
+      flag |= kFirstOpen | (open_right ? kBoth : 0);
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) my_part[(1 * V + v) * G + l] = acc[v];
+      if (l == 0) s_key[g * 2 + 1] = run_key;
+      flag |= kLastOpen;
+    }
+  }
+  __shared__ int s_stflag;
+  if (threadIdx.x == 0) s_stflag = 0;
+  if (l == 0) s_flag[g] = flag;
+  __syncthreads();
+
+  // ---- combine runs crossing tile borders inside the super-tile -------------
+  float* gpart = F.st_part + (size_t)st * 2 * dim;
+  int st_flag = 0;
+  if (g == 0 && (flag & kFirstOpen)) {
+    // chain entering from the previous super-tile
+    float4 acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = s_part[(size_t)(0 * 2 + 0) * V * G + v * G + l];
+    int t = 0;
+    bool both = true;
+    while (true) {
+      if (!(s_flag[t] & kBoth)) { both = false; break; }
+      ++t;
+      if (t == groups || !(s_flag[t] & kFirstOpen)) break;  // leaves the super-tile
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        acc[v] = f4_add_rn(acc[v], s_part[(size_t)(t * 2 + 0) * V * G + v * G + l]);
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      if (act[v]) *reinterpret_cast<float4*>(gpart + 0 * dim + col[v]) = acc[v];
+    if (l == 0) F.st_key[(size_t)st * 2 + 0] = s_key[0];
+    st_flag |= kFirstOpen | (both ? kBoth : 0);
+  }
+  if (flag & kLastOpen) {
+    // chain starting in my tile
+    float4 acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = s_part[(size_t)(g * 2 + 1) * V * G + v * G + l];
+    const uint32_t key = s_key[g * 2 + 1];
+    int t = g + 1;
+    bool closed = false;
+    while (t < groups) {
+      if (!(s_flag[t] & kFirstOpen)) break;  // (empty tail tile) -- cannot happen when open
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        acc[v] = f4_add_rn(acc[v], s_part[(size_t)(t * 2 + 0) * V * G + v * G + l]);
+      if (!(s_flag[t] & kBoth)) { closed = true; break; }
+      ++t;
+    }
+    if (closed) {
+      if (!apply_row<V>(P, F, key, acc, col, act)) oob = true;
+    } else {
+      // still open at the end of the super-tile
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (act[v]) *reinterpret_cast<float4*>(gpart + 1 * dim + col[v]) = acc[v];
+      if (l == 0) {
+        F.st_key[(size_t)st * 2 + 1] = key;
+        atomicOr(&s_stflag, kLastOpen);
+      }
+    }
+  }
+  if (g == 0 && l == 0 && st_flag) atomicOr(&s_stflag, st_flag);
+  if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
+  __syncthreads();
+  if (threadIdx.x == 0) F.st_flag[st] = s_stflag;
+}
+
+// Finish rows that span super-tiles: group per super-tile that STARTS a chain.
+template <int V>
+__global__ void __launch_bounds__(kUpdThreads)
+sparse_update_fixup_kernel(const __grid_constant__ UpdParams P) {
+  const int fi = find_upd_feat(P, blockIdx.x);
+  const UpdFeat& F = P.f[fi];
+  const int log2g = F.log2g;
+  const int G = 1 << log2g;
+  const int groups = kUpdThreads >> log2g;
+  const int g = threadIdx.x >> log2g;
+  const int l = threadIdx.x & (G - 1);
+  const int dim = F.dim;
+  const int st = (blockIdx.x - F.cta_begin) * groups + g;
+  if (st >= F.nst) return;
+  if (!(F.st_flag[st] & kLastOpen)) return;
+  int col[V];
+  bool act[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    col[v] = ((v << log2g) + l) * 4;
+    act[v] = col[v] < dim;
+  }
+  float4 acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v)
+    acc[v] = act[v] ? *reinterpret_cast<const float4*>(F.st_part + ((size_t)st * 2 + 1) * dim + col[v])
+                    : f4_zero();
+  const uint32_t key = F.st_key[(size_t)st * 2 + 1];
+  int t = st + 1;
+  while (t < F.nst) {
+    const int fl = F.st_flag[t];
+    if (!(fl & kFirstOpen)) break;
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      if (act[v])
+        acc[v] = f4_add_rn(acc[v], *reinterpret_cast<const float4*>(
+                                       F.st_part + ((size_t)t * 2 + 0) * dim + col[v]));
+    if (!(fl & kBoth)) break;
+    ++t;
+  }
+  if (!apply_row<V>(P, F, key, acc, col, act)) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
+}
+
+// bag index of every id position, for CSR features (thread per bag).
+struct BagMapFeat {
+  const int64_t* offsets;
+  int32_t* bag_of_pos;
+  int32_t nbags;
+  int32_t cta_begin;
+  int64_t nnz;
+};
+struct BagMapParams {
+  BagMapFeat f[kMaxUpdFeats];
+  int32_t* status;
+  int32_t nfeats;
+};
+
+__global__ void __launch_bounds__(256) bag_of_position_kernel(const __grid_constant__ BagMapParams P) {
+  int lo = 0, hi = P.nfeats - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (P.f[mid].cta_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const BagMapFeat& F = P.f[lo];
+  const int b = (blockIdx.x - F.cta_begin) * 256 + threadIdx.x;
+  if (b >= F.nbags) return;
+  int64_t s = F.offsets[b], e = F.offsets[b + 1];
+  if (s < 0 || e < s || e > F.nnz) { raise_status(P.status, HB_STATUS_BAD_OFFSETS); return; }
+  for (int64_t p = s; p < e; ++p) F.bag_of_pos[p] = b;
+}
+
+static int ilog2c(int64_t x) {
+  int l = 0;
+  while (((int64_t)1 << l) < x) ++l;
+  return l;
+}
+
+static void upd_shape(int dim, int* log2g, int* v) {
+  const int vecs = dim / 4;
+  if (vecs <= 32) { *log2g = ilog2c(vecs); *v = 1; return; }
+  *log2g = 5;
+  int vv = (vecs + 31) / 32, p = 1;
+  while (p < vv) p <<= 1;
+  *v = p;
+}
+
+constexpr int kRadixBits = 9;
+constexpr int kRadixBins = 1 << kRadixBits;
+
+static int tile_c(int V) { return V == 1 ? 8 : (V == 2 ? 4 : 2); }
+
+// per-feature workspace layout
+struct UpdLayout {
+  size_t keysA, keysB, valsA, valsB, bagmap, st_part, st_key, st_flag, end;
+  int passes, log2g, V, C, nst;
+};
+
+static UpdLayout upd_layout(const hbUpdateFeature& f, size_t base) {
+  UpdLayout L;
+  const size_t n = (size_t)f.nnz;
+  size_t o = base;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  L.keysA = take(4 * n); L.keysB = take(4 * n);
+  L.valsA = take(4 * n); L.valsB = take(4 * n);
+  L.bagmap = take(f.offsets ? 4 * n : 0);
+  upd_shape(f.dim, &L.log2g, &L.V);
+  L.C = tile_c(L.V);
+  const int groups = kUpdThreads >> L.log2g;
+  const int64_t per_st = (int64_t)groups * L.C;
+  L.nst = (int)((f.nnz + per_st - 1) / per_st);
+  L.st_part = take((size_t)L.nst * 2 * f.dim * 4);
+  L.st_key = take((size_t)L.nst * 2 * 4);
+  L.st_flag = take((size_t)L.nst * 4);
+  const int64_t local_rows = f.rows;
+  const int bits = local_rows > 1 ? ilog2c(local_rows) : 1;
+  L.passes = (bits + kRadixBits - 1) / kRadixBits;
+  if (L.passes < 1) L.passes = 1;
+  L.end = o;
+  return L;
+}
+
+template <int V, int C>
+static int launch_update(const UpdParams& P, int log2g_max, cudaStream_t stream) {
+  (void)log2g_max;
+  if (P.total_ctas == 0) return HB_OK;
+  // smem: groups*(2*V*G*16 + 12) with groups*G == 256
+  const size_t smem = (size_t)2 * V * kUpdThreads * 16 + (size_t)kUpdThreads * 12;
+  if (smem > 48 * 1024)
+    HB_CUDA_OK(cudaFuncSetAttribute(sparse_update_kernel<V, C>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    KernelScope ks(HB_K_SPARSE_UPDATE, stream);
+    sparse_update_kernel<V, C><<<P.total_ctas, kUpdThreads, smem, stream>>>(P);
+  }
+  HB_CUDA_OK(cudaGetLastError());
+  return HB_OK;
+}
+
+static int validate_upd(int k, const hbUpdateFeature& f, const hbOptimizer* opt) {
+  HB_REQUIRE(f.dim >= 4 && f.dim % 4 == 0 && f.dim <= 1024,
+             "update: feature %d dim %d must be a multiple of 4 in [4,1024]", k, f.dim);
+  HB_REQUIRE(f.nnz >= 0 && f.nnz <= INT32_MAX && f.nbags >= 0 && f.nbags <= INT32_MAX,
+             "update: feature %d bad nnz/nbags", k);
+  HB_REQUIRE(f.offsets != nullptr || f.nnz == f.nbags,
+             "update: feature %d has no offsets, so nnz must equal nbags", k);
+  HB_REQUIRE(f.rows >= 0 && f.rows < ((int64_t)1 << 32) - 1, "update: feature %d rows out of range", k);
+  HB_REQUIRE(f.id_div >= 1, "update: feature %d id_div must be >= 1", k);
+  HB_REQUIRE(f.grad_stride >= f.dim && f.grad_stride % 4 == 0,
+             "update: feature %d grad_stride must be a multiple of 4 and >= dim", k);
+  HB_REQUIRE(f.combiner >= HB_SUM && f.combiner <= HB_SQRTN, "update: feature %d bad combiner", k);
+  if (f.nnz > 0) {
+    HB_REQUIRE(f.table && f.ids && f.grad, "update: feature %d null pointer", k);
+    HB_REQUIRE(((uintptr_t)f.table & 15) == 0 && ((uintptr_t)f.grad & 15) == 0,
+               "update: feature %d table/grad must be 16-byte aligned", k);
+    if (opt->kind == HB_OPT_ADAGRAD)
+      HB_REQUIRE(f.slot0 != nullptr, "update: feature %d Adagrad needs slot0 (accumulator)", k);
+    if (opt->kind == HB_OPT_LAZY_ADAM)
+      HB_REQUIRE(f.slot0 != nullptr && f.slot1 != nullptr, "update: feature %d LazyAdam needs slot0/slot1", k);
+  }
+  return HB_OK;
+}
+
+// Sort (row, bag) pairs of every feature and run the fused update.  `ids_div`
+// is shared by the features of one call (1 locally, W on a row-interleaved shard).
+int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* opt, void* ws,
+                      size_t ws_bytes, int32_t* d_status, cudaStream_t stream) {
+  HB_REQUIRE(n >= 1 && feats && opt, "update: bad arguments");
+  HB_REQUIRE(opt->kind >= HB_OPT_SGD && opt->kind <= HB_OPT_LAZY_ADAM, "update: bad optimizer kind %d", opt->kind);
+  for (int k = 0; k < n; ++k) {
+    int rc = validate_upd(k, feats[k], opt);
+    if (rc != HB_OK) return rc;
+    HB_REQUIRE(feats[k].id_div == feats[0].id_div, "update: all features of a call must share id_div");
+  }
+  size_t need = 0;
+  int rc = hbGroupSparseUpdateWorkspaceBytes(n, feats, &need);
+  if (rc != HB_OK) return rc;
+  if (ws_bytes < need || (need > 0 && ws == nullptr)) {
+    set_last_error("update: workspace %zu < required %zu bytes", ws_bytes, need);
+    return HB_ERR_WORKSPACE;
+  }
+  unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+
+  for (int c0 = 0; c0 < n; c0 += kMaxUpdFeats) {
+    const int nc = (n - c0 < kMaxUpdFeats) ? n - c0 : kMaxUpdFeats;
+    // layouts
+    UpdLayout L[kMaxUpdFeats];
+    size_t off = 0;
+    {
+      // recompute the running offset of this chunk
+      for (int k = 0; k < c0; ++k) off = upd_layout(feats[k], off).end;
+    }
+    size_t o = off;
+    int total_tiles = 0, max_passes = 0;
+    for (int k = 0; k < nc; ++k) {
+      L[k] = upd_layout(feats[c0 + k], o);
+      o = L[k].end;
+      total_tiles += bucket_tiles(feats[c0 + k].nnz);
+      if (feats[c0 + k].nnz > 0 && L[k].passes > max_passes) max_passes = L[k].passes;
+    }
+    int32_t* counts = reinterpret_cast<int32_t*>(base + o);  // chunk-shared radix counters
+
+    // 1. bag map for CSR features
+    {
+      BagMapParams B;
+      B.status = d_status;
+      B.nfeats = 0;
+      int ctas = 0;
+      for (int k = 0; k < nc; ++k) {
+        const hbUpdateFeature& f = feats[c0 + k];
+        if (f.offsets == nullptr || f.nbags == 0) continue;
+        BagMapFeat& bf = B.f[B.nfeats++];
+        bf.offsets = f.offsets;
+        bf.bag_of_pos = reinterpret_cast<int32_t*>(base + L[k].bagmap);
+        bf.nbags = (int32_t)f.nbags;
+        bf.cta_begin = ctas;
+        bf.nnz = f.nnz;
+        ctas += (int)((f.nbags + 255) / 256);
+      }
+      if (ctas > 0) {
+        KernelScope ks(HB_K_BAG_MAP, stream);
+        bag_of_position_kernel<<<ctas, 256, 0, stream>>>(B);
+        HB_CUDA_OK(cudaGetLastError());
+      }
+    }
+
+    // 2. radix passes; feature k takes part in pass p iff p < passes[k]
+    for (int p = 0; p < max_passes; ++p) {
+      BucketParams bp;
+      bp.nsegs = 0;
+      int tiles = 0;
+      for (int k = 0; k < nc; ++k) {
+        const hbUpdateFeature& f = feats[c0 + k];
+        if (f.nnz == 0 || p >= L[k].passes) continue;
+        BucketSeg& s = bp.seg[bp.nsegs++];
+        uint32_t* kA = reinterpret_cast<uint32_t*>(base + L[k].keysA);
+        uint32_t* kB = reinterpret_cast<uint32_t*>(base + L[k].keysB);
+        int32_t* vA = reinterpret_cast<int32_t*>(base + L[k].valsA);
+        int32_t* vB = reinterpret_cast<int32_t*>(base + L[k].valsB);
+        if (p == 0) {
+          s.in_keys = f.ids;
+          s.in_vals = f.offsets ? reinterpret_cast<int32_t*>(base + L[k].bagmap) : nullptr;
+          s.out_keys = kA;
+          s.out_vals = vA;
+        } else {
+          const bool a2b = (p & 1) == 1;  // pass 1: A->B, pass 2: B->A, ...
+          s.in_keys = a2b ? kA : kB;
+          s.in_vals = a2b ? vA : vB;
+          s.out_keys = a2b ? kB : kA;
+          s.out_vals = a2b ? vB : vA;
+        }
+        s.out_inv = nullptr;
+        s.out_sizes = nullptr;
+        s.n = (int32_t)f.nnz;
+        s.tile_begin = tiles;
+        s.shift = p * kRadixBits;
+        s.key_limit = (uint32_t)f.rows;
+        tiles += bucket_tiles(f.nnz);
+      }
+      if (bp.nsegs == 0) break;
+      bp.counts = counts;
+      bp.nbins = kRadixBins;
+      bp.total_tiles = tiles;
+      bp.p = 1; bp.m = 1; bp.pow2_mask = 0;
+      bp.div = feats[0].id_div;
+      bp.div_shift = ((bp.div & (bp.div - 1)) == 0 && bp.div <= (1 << 30)) ? ilog2c(bp.div) : -1;
+      bp.pad = 0;
+      rc = (p == 0) ? bucket_pass_launch<RadixFirstTraits>(bp, stream, HB_K_SORT_COUNT)
+                    : bucket_pass_launch<RadixNextTraits>(bp, stream, HB_K_SORT_COUNT);
+      if (rc != HB_OK) return rc;
+    }
+
+    // 3./4. fused update + fix-up, one launch per V
+    for (int V = 1; V <= 8; V <<= 1) {
+      UpdParams U;
+      U.status = d_status;
+      U.nfeats = 0;
+      U.total_ctas = 0;
+      U.opt = opt->kind;
+      U.lr = opt->lr;
+      U.beta1 = opt->beta1; U.beta2 = opt->beta2; U.eps = opt->eps;
+      U.omb1 = 1.0f - opt->beta1; U.omb2 = 1.0f - opt->beta2;
+      if (opt->kind == HB_OPT_LAZY_ADAM) {
+        const double t = (double)(opt->step < 1 ? 1 : opt->step);
+        U.lr = (float)((double)opt->lr * sqrt(1.0 - pow((double)opt->beta2, t)) /
+                       (1.0 - pow((double)opt->beta1, t)));
+      }
+      int fix_ctas = 0;
+      int fix_begin[kMaxUpdFeats];
+      for (int k = 0; k < nc; ++k) {
+        const hbUpdateFeature& f = feats[c0 + k];
+        if (L[k].V != V || f.nnz == 0) continue;
+        UpdFeat& F = U.f[U.nfeats];
+        const bool inA = (L[k].passes & 1) == 1;  // 1 pass -> A, 2 -> B, 3 -> A, ...
+        F.table = f.table; F.slot0 = f.slot0; F.slot1 = f.slot1;
+        F.grad = f.grad; F.offsets = f.offsets;
+        F.keys = reinterpret_cast<uint32_t*>(base + (inA ? L[k].keysA : L[k].keysB));
+        F.bags = reinterpret_cast<int32_t*>(base + (inA ? L[k].valsA : L[k].valsB));
+        F.st_part = reinterpret_cast<float*>(base + L[k].st_part);
+        F.st_key = reinterpret_cast<uint32_t*>(base + L[k].st_key);
+        F.st_flag = reinterpret_cast<int32_t*>(base + L[k].st_flag);
+        F.rows = f.rows; F.grad_stride = f.grad_stride;
+        F.n = (int32_t)f.nnz; F.dim = f.dim; F.combiner = f.combiner;
+        F.log2g = L[k].log2g;
+        F.cta_begin = U.total_ctas;
+        F.nst = L[k].nst;
+        U.total_ctas += L[k].nst;
+        const int groups = kUpdThreads >> L[k].log2g;
+        fix_begin[U.nfeats] = fix_ctas;
+        fix_ctas += (L[k].nst + groups - 1) / groups;
+        U.nfeats++;
+      }
+      if (U.nfeats == 0) continue;
+      switch (V) {
+        case 1: rc = launch_update<1, 8>(U, 0, stream); break;
+        case 2: rc = launch_update<2, 4>(U, 0, stream); break;
+        case 4: rc = launch_update<4, 2>(U, 0, stream); break;
+        default: rc = launch_update<8, 2>(U, 0, stream); break;
+      }
+      if (rc != HB_OK) return rc;
+      // fix-up launch: same params, cta_begin re-based to fix-up CTAs
+      UpdParams X = U;
+      for (int k = 0; k < X.nfeats; ++k) X.f[k].cta_begin = fix_begin[k];
+      X.total_ctas = fix_ctas;
+      if (fix_ctas > 0) {
+        KernelScope ks(HB_K_SPARSE_FIXUP, stream);
+        switch (V) {
+          case 1: sparse_update_fixup_kernel<1><<<fix_ctas, kUpdThreads, 0, stream>>>(X); break;
+          case 2: sparse_update_fixup_kernel<2><<<fix_ctas, kUpdThreads, 0, stream>>>(X); break;
+          case 4: sparse_update_fixup_kernel<4><<<fix_ctas, kUpdThreads, 0, stream>>>(X); break;
+          default: sparse_update_fixup_kernel<8><<<fix_ctas, kUpdThreads, 0, stream>>>(X); break;
+        }
+        HB_CUDA_OK(cudaGetLastError());
+      }
+    }
+  }
+  return HB_OK;
+}
+
+}  // namespace hb
+
+extern "C" {
+
+int hbGroupSparseUpdateWorkspaceBytes(int n, const hbUpdateFeature* feats, size_t* bytes) {
+  using namespace hb;
+  HB_REQUIRE(n >= 1 && feats && bytes, "hbGroupSparseUpdateWorkspaceBytes: bad argument");
+  size_t o = 0;
+  size_t max_chunk_counts = 0;
+  for (int c0 = 0; c0 < n; c0 += kMaxUpdFeats) {
+    const int nc = (n - c0 < kMaxUpdFeats) ? n - c0 : kMaxUpdFeats;
+    size_t tiles = 0;
+    for (int k = 0; k < nc; ++k) {
+      const hbUpdateFeature& f = feats[c0 + k];
+      HB_REQUIRE(f.nnz >= 0 && f.nnz <= INT32_MAX && f.dim >= 4 && f.dim % 4 == 0 && f.dim <= 1024,
+                 "hbGroupSparseUpdateWorkspaceBytes: feature %d bad nnz/dim", c0 + k);
+      o = upd_layout(f, o).end;
+      tiles += bucket_tiles(f.nnz);
+    }
+    const size_t cb = align_up(tiles * kRadixBins * sizeof(int32_t), 256);
+    if (cb > max_chunk_counts) max_chunk_counts = cb;
+  }
+  *bytes = o + max_chunk_counts + 256;
+  return HB_OK;
+}
+
+int hbGroupLookupBackwardUpdate(int n, const hbUpdateFeature* feats, const hbOptimizer* opt,
+                                void* d_workspace, size_t workspace_bytes, int32_t* d_status,
+                                hbStream stream) {
+  return hb::sparse_update_run(n, feats, opt, d_workspace, workspace_bytes, d_status,
+                               (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+"""embedding_lookup_sparse / GroupLookup: host side of K3 (gather+pool), K5
+(backward + sparse optimizer) and of the fused sharded path (K1+K2+K3+K4).
+
+Mirrors what `tf.nn.embedding_lookup_sparse` computes under
+`hb.embedding_scope()` (hybridbackend/tensorflow/embedding/sharding.py:168-205):
+sparse ids are given in CSR form (values + bag offsets; a TF SparseTensor's
+`indices[:, 0]` converts with `segment_ids_to_offsets`), `sp_weights` is None and
+the default combiner is "mean" as in TF-1.15.
+"""
+import torch
+
+from hybridbackend_b200 import _lib
+from hybridbackend_b200 import _util
+from hybridbackend_b200.embedding.sharding import ShardedEmbeddingWeights
+
+
+def segment_ids_to_offsets(segment_ids, nbags):
+  """Sorted int segment ids [nnz] (SparseTensor.indices[:, 0]) -> offsets
+  [nbags+1] int64.  Data-prep convenience (torch ops), not part of the hot path."""
+  seg = segment_ids.to(torch.int64)
+  bounds = torch.arange(nbags + 1, device=seg.device, dtype=torch.int64)
+  return torch.searchsorted(seg, bounds, right=False).to(torch.int64)
+
+
+def _weight_of(params):
+  return params.weight if isinstance(params, ShardedEmbeddingWeights) else params
+
+
+def _feature_struct(weight, ids, offsets, nbags, out, out_stride, combiner, id_div=1):
+  return _lib.hbLookupFeature(
+      weight.data_ptr(), weight.shape[0], ids.data_ptr(),
+      offsets.data_ptr() if offsets is not None else None, nbags, out.data_ptr(),
+      out_stride, weight.shape[1], _lib.COMBINER[combiner], id_div)
+
+
+def _check_inputs(weight, ids, offsets, what):
+  _util.require_cuda(weight, f'{what}: params')
+  _util.require_cuda(ids, f'{what}: ids')
+  if weight.dtype != torch.float32 or weight.dim() != 2:
+    raise TypeError(f'{what}: params must be a 2-D float32 tensor')
+  if ids.dtype != torch.int64 or ids.dim() != 1:
+    raise TypeError(f'{what}: ids must be a 1-D int64 tensor')
+  if offsets is not None:
+    _util.require_cuda(offsets, f'{what}: offsets')
+    if offsets.dtype != torch.int64 or offsets.dim() != 1 or offsets.numel() < 1:
+      raise TypeError(f'{what}: offsets must be a 1-D int64 tensor of nbags+1 entries')
+
+
+def embedding_lookup_sparse(params, ids, offsets=None, sp_weights=None, combiner=None,
+                            out=None, check=False):
+  """Pooled lookup of one feature: out[b] = combine(params[ids[offsets[b]:offsets[b+1]]]).
+
+  offsets=None means one id per bag.  combiner defaults to "mean" (TF-1.15)."""
+  if sp_weights is not None:
+    raise NotImplementedError('sp_weights is not on the hot path (the reference '
+                              'call sites pass None)')
+  combiner = combiner or 'mean'
+  if combiner not in _lib.COMBINER:
+    raise ValueError('combiner must be one of "mean", "sqrtn" or "sum"')
+  weight = _weight_of(params)
+  _check_inputs(weight, ids, offsets, 'embedding_lookup_sparse')
+  nbags = ids.numel() if offsets is None else offsets.numel() - 1
+  dim = weight.shape[1]
+  if out is None:
+    out = torch.empty(nbags, dim, dtype=torch.float32, device=weight.device)
+  feat = (_lib.hbLookupFeature * 1)(
+      _feature_struct(weight, ids, offsets, nbags, out, out.stride(0), combiner))
+  st = _util.status_word(weight.device)
+  with torch.cuda.device(weight.device):
+    _lib.check(_lib.lib().hbGroupLookupForward(1, feat, _lib.C.c_void_p(st.data_ptr()),
+                                               _util.stream_ptr()),
+               'embedding_lookup_sparse')
+  if check:
+    _util.check_status(weight.device)
+  return out
+
+
+def embedding_lookup(params, ids, check=False):
+  """tf.nn.embedding_lookup on a local table: out[i] = params[ids[i]]."""
+  return embedding_lookup_sparse(params, ids.reshape(-1), None, combiner='sum', check=check)
+
+
+class GroupLookup:
+  """All sparse features of a model looked up (and updated) together.
+
+  Single rank / replicated tables: one fused gather+pool launch writes straight
+  into the concatenated `[B, sum(dim)]` dense-MLP input; `backward_update` sorts
+  the ids once and applies the sparse optimizer in one fused pass per row.
+  With a `Collective` (world_size > 1) sharded tables go through the fused
+  partition -> NVSwitch push -> owner gather -> stitch path
+  (embedding/sharding.py:171-203 composition; see hb_b200.h).
+  """
+
+  def __init__(self, tables, combiners=None, collective=None, max_nnz=None,
+               capacity_factor=None):
+    self.tables = list(tables)
+    self.n = len(self.tables)
+    if self.n < 1:
+      raise ValueError('GroupLookup needs at least one table')
+    self.combiners = list(combiners) if combiners is not None else ['mean'] * self.n
+    self.dims = [_weight_of(t).shape[1] for t in self.tables]
+    self.col_offsets = [0]
+    for d in self.dims:
+      self.col_offsets.append(self.col_offsets[-1] + d)
+    self.out_dim = self.col_offsets[-1]
+    self.device = _weight_of(self.tables[0]).device
+    self.collective = collective
+    self._saved = None
+    self._sharded = None
+    world = collective.world_size if collective is not None else 1
+    self.sharded_idx = [k for k, t in enumerate(self.tables)
+                        if world > 1 and isinstance(t, ShardedEmbeddingWeights) and t.sharded]
+    self.local_idx = [k for k in range(self.n) if k not in self.sharded_idx]
+    if self.sharded_idx:
+      from hybridbackend_b200.embedding.sharded import ShardedGroup  # pylint: disable=import-outside-toplevel
+      if max_nnz is None:
+        raise ValueError('GroupLookup with sharded tables needs max_nnz (static bound '
+                         'of ids per feature per rank)')
+      self._sharded = ShardedGroup(
+          collective, [self.tables[k] for k in self.sharded_idx],
+          [self.combiners[k] for k in self.sharded_idx],
+          [max_nnz[k] for k in self.sharded_idx], capacity_factor)
+
+  # -- forward ---------------------------------------------------------------
+  def forward(self, ids, offsets=None, out=None, check=False):
+    """ids[k]: int64 [nnz_k]; offsets[k]: int64 [B+1] or None.  Returns
+    out [B, sum(dim)] float32 (feature k occupies columns col_offsets[k]:+dim)."""
+    offsets = list(offsets) if offsets is not None else [None] * self.n
+    nbags = [ids[k].numel() if offsets[k] is None else offsets[k].numel() - 1
+             for k in range(self.n)]
+    B = nbags[0]
+    if any(b != B for b in nbags):
+      raise ValueError('all features of a GroupLookup must have the same number of bags')
+    for k in range(self.n):
+      _check_inputs(_weight_of(self.tables[k]), ids[k], offsets[k], f'GroupLookup feature {k}')
+    if out is None:
+      out = torch.empty(B, self.out_dim, dtype=torch.float32, device=self.device)
+    st = _util.status_word(self.device)
+    L = _lib.lib()
+    with torch.cuda.device(self.device):
+      if self.local_idx:
+        feats = (_lib.hbLookupFeature * len(self.local_idx))()
+        for j, k in enumerate(self.local_idx):
+          feats[j] = _feature_struct(_weight_of(self.tables[k]), ids[k], offsets[k], B,
+                                     out[:, self.col_offsets[k]:], out.stride(0),
+                                     self.combiners[k])
+        _lib.check(L.hbGroupLookupForward(len(self.local_idx), feats,
+                                          _lib.C.c_void_p(st.data_ptr()), _util.stream_ptr()),
+                   'GroupLookup.forward')
+      if self._sharded is not None:
+        self._sharded.forward([ids[k] for k in self.sharded_idx],
+                              [offsets[k] for k in self.sharded_idx], B, out,
+                              [self.col_offsets[k] for k in self.sharded_idx], st)
+    self._saved = (list(ids), offsets, B)
+    if check:
+      _util.check_status(self.device)
+    return out
+
+  def forward_host(self, h_ids, d_stage, out, h_out, check=False):
+    """Host-buffer forward (one id per bag): h_ids pinned int64 [n, B] is copied
+    H2D into d_stage [n, B], the fused lookup runs, and `out` [B, sum(dim)]
+    (contiguous, device) is copied D2H into pinned h_out -- all enqueued on the
+    current stream by ONE C-ABI call (hbGroupLookupForwardHost)."""
+    if not (h_ids.is_pinned() and h_out.is_pinned()):
+      raise ValueError('forward_host needs pinned host tensors')
+    if h_ids.dtype != torch.int64 or h_ids.dim() != 2 or h_ids.shape[0] != self.n:
+      raise TypeError('h_ids must be pinned int64 [n_features, B]')
+    B = h_ids.shape[1]
+    _util.require_cuda(d_stage, 'forward_host: d_stage')
+    _util.require_cuda(out, 'forward_host: out')
+    if d_stage.shape != h_ids.shape or d_stage.dtype != torch.int64:
+      raise ValueError('d_stage must be an int64 device tensor shaped like h_ids')
+    if tuple(out.shape) != (B, self.out_dim) or tuple(h_out.shape) != (B, self.out_dim):
+      raise ValueError('out / h_out must be [B, sum(dim)]')
+    st = _util.status_word(self.device)
+    L = _lib.lib()
+    ids = [d_stage[k] for k in range(self.n)]
+    with torch.cuda.device(self.device):
+      if self._sharded is None:
+        feats = (_lib.hbLookupFeature * self.n)()
+        for k in range(self.n):
+          feats[k] = _feature_struct(_weight_of(self.tables[k]), ids[k], None, B,
+                                     out[:, self.col_offsets[k]:], out.stride(0),
+                                     self.combiners[k])
+        _lib.check(L.hbGroupLookupForwardHost(
+            self.n, feats, _lib.C.c_void_p(h_ids.data_ptr()), _lib.C.c_void_p(d_stage.data_ptr()),
+            _lib.C.c_size_t(h_ids.numel() * 8), _lib.C.c_void_p(out.data_ptr()),
+            _lib.C.c_void_p(h_out.data_ptr()), _lib.C.c_size_t(out.numel() * 4),
+            _lib.C.c_void_p(st.data_ptr()), _util.stream_ptr()), 'GroupLookup.forward_host')
+        self._saved = (ids, [None] * self.n, B)
+      else:
+        d_stage.copy_(h_ids, non_blocking=True)
+        self.forward(ids, out=out)
+        h_out.copy_(out, non_blocking=True)
+    if check:
+      _util.check_status(self.device)
+    return h_out
+
+  # -- backward + sparse optimizer apply ------------------------------------------
+  def backward_update(self, grad, optimizer, check=False):
+    """grad: [B, sum(dim)] upstream gradient of forward()'s output.  Applies
+    `optimizer` to every table in place (slots are created on first use)."""
+    if self._saved is None:
+      raise RuntimeError('GroupLookup.backward_update called before forward')
+    ids, offsets, B = self._saved
+    _util.require_cuda(grad, 'GroupLookup.backward_update: grad')
+    if grad.dtype != torch.float32 or grad.dim() != 2 or grad.shape[0] != B or \
+        grad.shape[1] != self.out_dim or grad.stride(1) != 1:
+      raise ValueError('grad must be float32 [B, sum(dim)] with unit inner stride')
+    optimizer.step += 1
+    desc = optimizer.descriptor()
+    st = _util.status_word(self.device)
+    L = _lib.lib()
+    with torch.cuda.device(self.device):
+      if self.local_idx:
+        m = len(self.local_idx)
+        feats = (_lib.hbUpdateFeature * m)()
+        for j, k in enumerate(self.local_idx):
+          t = self.tables[k]
+          w = _weight_of(t)
+          slots = self._slots(k, optimizer)
+          feats[j] = _lib.hbUpdateFeature(
+              w.data_ptr(), slots[0].data_ptr() if len(slots) > 0 else None,
+              slots[1].data_ptr() if len(slots) > 1 else None, w.shape[0],
+              ids[k].data_ptr(), offsets[k].data_ptr() if offsets[k] is not None else None,
+              B, ids[k].numel(), grad[:, self.col_offsets[k]:].data_ptr(), grad.stride(0),
+              w.shape[1], _lib.COMBINER[self.combiners[k]], 1)
+        need = _lib.C.c_size_t(0)
+        _lib.check(L.hbGroupSparseUpdateWorkspaceBytes(m, feats, _lib.C.byref(need)),
+                   'GroupLookup.backward_update')
+        ws = _util.workspace(need.value, self.device, 'update')
+        _lib.check(L.hbGroupLookupBackwardUpdate(
+            m, feats, _lib.C.byref(desc), _lib.C.c_void_p(ws.data_ptr()),
+            _lib.C.c_size_t(ws.numel()), _lib.C.c_void_p(st.data_ptr()), _util.stream_ptr()),
+                   'GroupLookup.backward_update')
+      if self._sharded is not None:
+        self._sharded.backward_update(grad, [self.col_offsets[k] for k in self.sharded_idx],
+                                      optimizer, desc, st)
+    if check:
+      _util.check_status(self.device)
+
+  def _slots(self, k, optimizer):
+    t = self.tables[k]
+    if isinstance(t, ShardedEmbeddingWeights):
+      return t.ensure_slots(optimizer)
+    if not hasattr(self, '_raw_slots'):
+      self._raw_slots = {}
+    s = self._raw_slots.setdefault(k, [])
+    while len(s) < optimizer.num_slots:
+      s.append(torch.full_like(t, optimizer.slot_init(len(s))))
+    return s
+
+  def slots(self, k):
+    t = self.tables[k]
+    if isinstance(t, ShardedEmbeddingWeights):
+      return t.slots
+    return getattr(self, '_raw_slots', {}).get(k, [])

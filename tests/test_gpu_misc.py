@@ -1,0 +1,64 @@
+"""Cast (wire dtype) and slab-hash cache probe parity on the GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cast_n(hb):
+  L = hb._lib.lib()
+  xs = [torch.randn(n, device='cuda') for n in (0, 1, 2049, 100000)]
+  hs = [torch.empty(x.numel(), dtype=torch.float16, device='cuda') for x in xs]
+  st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+  cnt = hb._lib.i64_array([x.numel() for x in xs])
+  assert L.hbCastN(4, hb._lib.ptr_array([x.data_ptr() for x in xs]),
+                   hb._lib.ptr_array([h.data_ptr() for h in hs]), cnt, 4, 5, st) == 0
+  back = [torch.empty_like(x) for x in xs]
+  assert L.hbCastN(4, hb._lib.ptr_array([h.data_ptr() for h in hs]),
+                   hb._lib.ptr_array([b.data_ptr() for b in back]), cnt, 5, 4, st) == 0
+  for x, h, b in zip(xs, hs, back):
+    assert torch.equal(h, x.half()) and torch.equal(b, x.half().float())
+
+
+def _build_cache(oracle, slabs, keys):
+  empty = np.iinfo(np.int64).min
+  cache = np.full(slabs * 32, empty, np.int64)
+  for k in keys:
+    s = oracle.murmur3_hash32(int(k)) % slabs
+    for _ in range(slabs):
+      row = cache[s * 32:(s + 1) * 32]
+      free = np.where(row == empty)[0]
+      if len(free):
+        row[free[0]] = k
+        break
+      s = (s + 1) % slabs
+  return cache
+
+
+@pytest.mark.parametrize('slabs,nkeys', [(7, 150), (64, 1500), (3, 96)])
+def test_cache_lookup(hb, oracle, slabs, nkeys):
+  """HbLookup semantics (embedding/lookup_functors.cu.cc:53-149), compared as sets."""
+  rng = np.random.RandomState(slabs)
+  present = rng.choice(10**6, size=min(nkeys, slabs * 32), replace=False).astype(np.int64)
+  cache = _build_cache(oracle, slabs, present)
+  q = np.concatenate([rng.choice(present, 700), rng.randint(10**6, 2 * 10**6, 300)]).astype(np.int64)
+  rng.shuffle(q)
+  n = len(q)
+  L = hb._lib.lib()
+  d_cache, d_q = torch.from_numpy(cache).cuda(), torch.from_numpy(q).cuda()
+  idx = torch.full((n,), -1, dtype=torch.int32, device='cuda')
+  pay = torch.full((n,), -1, dtype=torch.int64, device='cuda')
+  cnt = torch.zeros(2, dtype=torch.int32, device='cuda')
+  rc = L.hbCacheLookup(C.c_void_p(d_cache.data_ptr()), C.c_int64(slabs), C.c_void_p(d_q.data_ptr()), n,
+                       C.c_void_p(idx.data_ptr()), C.c_void_p(pay.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                       C.c_void_p(torch.cuda.current_stream().cuda_stream))
+  assert rc == 0
+  nm, nh = cnt.tolist()
+  hi, hc, mi, mk = oracle.cache_lookup(cache, q)
+  assert nm == len(mi) and nh == len(hi) and nm + nh == n
+  idx, pay = idx.cpu().numpy(), pay.cpu().numpy()
+  assert set(zip(idx[:nh].tolist(), pay[:nh].tolist())) == set(zip(hi.tolist(), hc.tolist()))
+  assert set(zip(idx[n - nm:].tolist(), pay[n - nm:].tolist())) == set(zip(mi.tolist(), mk.tolist()))

@@ -1,0 +1,122 @@
+"""K5 parity (GPU): backward + sparse optimizer vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _bags(rng, nb, rows, mean_len=3):
+  lens = rng.poisson(mean_len, nb) + 1
+  offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+  ids = rng.randint(0, rows, int(offsets[-1])).astype(np.int64)
+  return ids, offsets
+
+
+def _oracle_step(oracle, opt, tables, slots, feats, grad, cols, combiner, step):
+  for k, (ids, off) in enumerate(feats):
+    D = tables[k].shape[1]
+    g = np.ascontiguousarray(grad[:, cols[k]:cols[k] + D])
+    if off is None:
+      off = np.arange(len(ids) + 1, dtype=np.int64)
+    rg = oracle.lookup_row_grads(g, off, combiner)
+    if opt == 'adagrad':
+      oracle.sparse_apply_adagrad(tables[k], slots[k][0], ids, rg, 0.01)
+    elif opt == 'lazy_adam':
+      oracle.sparse_apply_lazy_adam(tables[k], slots[k][0], slots[k][1], ids, rg, 0.001, 0.9, 0.999,
+                                    1e-8, step)
+
+
+def _run(hb, oracle, opt, combiner, rows_list, D, B, steps=2, one_hot=False, zipf=False, seed=0):
+  rng = np.random.RandomState(seed)
+  n = len(rows_list)
+  tables = [rng.uniform(-1e-1, 1e-1, (r, D)).astype(np.float32) for r in rows_list]
+  dev_tables = [torch.from_numpy(t.copy()).cuda() for t in tables]
+  if opt == 'adagrad':
+    optimizer = hb.training.Adagrad(0.01)
+    slots = [[np.full_like(t, 0.1)] for t in tables]
+  else:
+    optimizer = hb.training.LazyAdam(0.001)
+    slots = [[np.zeros_like(t), np.zeros_like(t)] for t in tables]
+  gl = hb.embedding.GroupLookup(dev_tables, [combiner] * n)
+  cols = [k * D for k in range(n)]
+  for step in range(1, steps + 1):
+    feats = []
+    for r in rows_list:
+      if one_hot:
+        ids = (rng.zipf(1.3, B) % r if zipf else rng.randint(0, r, B)).astype(np.int64)
+        feats.append((ids, None))
+      else:
+        feats.append(_bags(rng, B, r))
+    grad = rng.randn(B, n * D).astype(np.float32)
+    gl.forward([torch.from_numpy(f[0]).cuda() for f in feats],
+               None if one_hot else [torch.from_numpy(f[1]).cuda() for f in feats])
+    gl.backward_update(torch.from_numpy(grad).cuda(), optimizer, check=True)
+    _oracle_step(oracle, opt, tables, slots, feats, grad, cols, combiner, step)
+  for k in range(n):
+    got = dev_tables[k].cpu().numpy()
+    np.testing.assert_allclose(got, tables[k], rtol=RTOL, atol=1e-6, err_msg=f'table {k}')
+    for s_dev, s_ref in zip(gl.slots(k), slots[k]):
+      np.testing.assert_allclose(s_dev.cpu().numpy(), s_ref, rtol=RTOL, atol=1e-6)
+  return dev_tables, tables
+
+
+@pytest.mark.parametrize('combiner', ['mean', 'sum', 'sqrtn'])
+def test_adagrad_c1(hb, oracle, combiner):
+  _run(hb, oracle, 'adagrad', combiner, [100000] * 4, 16, 4096)
+
+
+def test_adagrad_one_hot_no_dups_bit_exact(hb, oracle):
+  # rows >> B: almost no duplicates -> identical op sequence -> bit-exact expected
+  dev, ref = _run(hb, oracle, 'adagrad', 'mean', [3000000, 500000], 32, 8192, one_hot=True)
+  for d, r in zip(dev, ref):
+    assert np.array_equal(d.cpu().numpy(), r)
+
+
+def test_adagrad_hot_rows_tiny_tables(hb, oracle):
+  # Criteo has tables of 3..155 rows: thousands of duplicates per row, rows span
+  # many tiles and super-tiles (exercises the in-CTA combine and the fix-up kernel)
+  _run(hb, oracle, 'adagrad', 'mean', [3, 4, 10, 63, 155, 976], 32, 20000, one_hot=True)
+
+
+def test_adagrad_zipf(hb, oracle):
+  _run(hb, oracle, 'adagrad', 'mean', [1543, 39043, 403346], 32, 30000, one_hot=True, zipf=True)
+
+
+@pytest.mark.parametrize('dim', [4, 16, 64, 128, 256])
+def test_adagrad_dims(hb, oracle, dim):
+  _run(hb, oracle, 'adagrad', 'sum', [5000, 700], dim, 3000, steps=1)
+
+
+def test_lazy_adam(hb, oracle):
+  _run(hb, oracle, 'lazy_adam', 'mean', [20000, 300], 16, 5000, steps=3)
+  _run(hb, oracle, 'lazy_adam', 'sum', [100000], 128, 4096, steps=2, one_hot=True, zipf=True)
+
+
+def test_determinism(hb):
+  """Same inputs -> bit-identical tables (no float atomics)."""
+  res = []
+  for _ in range(2):
+    g = torch.Generator(device='cuda').manual_seed(7)
+    t = torch.randn(1000, 32, device='cuda', generator=g)
+    ids = torch.randint(0, 1000, (50000,), device='cuda', generator=g)
+    grad = torch.randn(50000, 32, device='cuda', generator=g)
+    gl = hb.embedding.GroupLookup([t])
+    gl.forward([ids])
+    gl.backward_update(grad, hb.training.Adagrad(0.01))
+    res.append(t.clone())
+  assert torch.equal(res[0], res[1])
+
+
+def test_untouched_rows_unchanged_and_oob(hb):
+  t = torch.randn(100, 8, device='cuda')
+  t0 = t.clone()
+  gl = hb.embedding.GroupLookup([t], ['sum'])
+  ids = torch.tensor([5, 7, 5], device='cuda')
+  gl.forward([ids])
+  gl.backward_update(torch.ones(3, 8, device='cuda'), hb.training.SGD(0.5), check=True)
+  mask = torch.ones(100, dtype=torch.bool)
+  mask[[5, 7]] = False
+  assert torch.equal(t.cpu()[mask], t0.cpu()[mask])
+  assert torch.allclose(t[5], t0[5] - 1.0) and torch.allclose(t[7], t0[7] - 0.5)

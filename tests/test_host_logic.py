@@ -1,0 +1,118 @@
+"""Host-side logic on CPU: sharding rule vs the oracle, optimizer descriptors,
+and the world_size-2 recipe over gloo (the oracle's per-rank functions as the
+compute, torch.distributed/gloo as the transport) against the in-process
+W-rank simulator and the unsharded lookup."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_shard_rule_matches_oracle(hb, oracle):
+  from hybridbackend_b200.embedding import sharding
+  for n in (1, 5, 8, 9, 65536, 65537, 39884406):
+    for w in (1, 2, 3, 8):
+      for s in range(w):
+        assert sharding.shard_rows(n, w, s) == oracle.shard_rows(n, w, s)
+        assert sharding.shard_offset(n, w, s) == oracle.shard_offset(n, w, s)
+      for b in (-1, 100, 65536):
+        assert sharding.is_small_table(n, w, b) == oracle.is_small_table(n, w, b)
+
+
+def test_criteo_small_table_count(hb):
+  """with batch_size=65536, 18 of the 26 Criteo tables replicate."""
+  from conftest import criteo_table_sizes
+  from hybridbackend_b200.embedding import sharding
+  sizes = criteo_table_sizes()
+  assert len(sizes) == 26
+  assert sum(sharding.is_small_table(n, 8, 65536) for n in sizes) == 18
+  assert sum(sharding.is_small_table(n, 8, -1) for n in sizes) == 2  # rows <= W only
+
+
+def test_optimizer_descriptors(hb):
+  a = hb.training.Adagrad(0.01)
+  assert a.num_slots == 1 and a.slot_init(0) == pytest.approx(0.1)
+  d = a.descriptor()
+  assert d.kind == 1 and d.lr == pytest.approx(0.01)
+  l = hb.training.LazyAdam(0.001)
+  l.step = 3
+  d = l.descriptor()
+  assert d.kind == 2 and d.step == 3 and d.beta2 == pytest.approx(0.999)
+
+
+def test_segment_ids_to_offsets(hb):
+  seg = torch.tensor([0, 0, 2, 2, 2, 5])
+  off = hb.embedding.segment_ids_to_offsets(seg, 7)
+  assert off.tolist() == [0, 2, 2, 5, 5, 5, 6, 6]
+
+
+def _free_port():
+  s = socket.socket()
+  s.bind(('127.0.0.1', 0))
+  p = s.getsockname()[1]
+  s.close()
+  return p
+
+
+def _gloo_worker(rank, world, port, q):
+  import sys
+  sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+  from oracle import hb_oracle as o
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    rng = np.random.RandomState(100)
+    N, D = 1001, 8
+    table = rng.randn(N, D).astype(np.float32)          # same on all ranks
+    shard = np.ascontiguousarray(table[rank::world])    # embedding/variables.py:107-111
+    ids = np.random.RandomState(200 + rank).randint(0, N, 300 + 17 * rank).astype(np.int64)
+    # sharding.py:179-180 partition
+    part, sizes, idx = o.partition_by_modulo(ids, world)
+    # :181-182 alltoallv(ids): sizes exchange then payload, over gloo
+    send_sizes = torch.from_numpy(sizes.astype(np.int64))
+    recv_sizes = torch.empty(world, dtype=torch.int64)
+    dist.all_to_all_single(recv_sizes, send_sizes)
+    recv = torch.empty(int(recv_sizes.sum()), dtype=torch.int64)
+    dist.all_to_all_single(recv, torch.from_numpy(part), recv_sizes.tolist(), send_sizes.tolist())
+    # :183-192 owner side
+    u, inv = o.unique(recv.numpy())
+    emb = shard[u // world][inv]
+    # :193-196 return alltoallv with the received sizes
+    back = torch.empty(len(ids), D)
+    dist.all_to_all_single(back, torch.from_numpy(np.ascontiguousarray(emb)),
+                           send_sizes.tolist(), recv_sizes.tolist())
+    out = back.numpy()[idx]                              # :197-199 stitch
+    ok = bool(np.array_equal(out, table[ids]))
+    # token all-gather used by Collective's bootstrap
+    toks = [None] * world
+    dist.all_gather_object(toks, bytes([rank]) * 128)
+    ok = ok and b''.join(toks) == bytes([0]) * 128 + bytes([1]) * 128
+    q.put((rank, ok, recv_sizes.tolist()))
+  finally:
+    dist.destroy_process_group()
+
+
+def test_sharded_recipe_over_gloo_world2(oracle):
+  world = 2
+  ctx = mp.get_context('spawn')
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=120) for _ in range(world)]
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  assert all(ok for _, ok, _ in res)
+  # cross-check the exchanged sizes against the in-process simulator
+  ids = [np.random.RandomState(200 + r).randint(0, 1001, 300 + 17 * r).astype(np.int64)
+         for r in range(world)]
+  sizes = np.stack([oracle.partition_by_modulo(i, world)[1] for i in ids])
+  for rank, _, rs in res:
+    assert rs == sizes[:, rank].tolist()
