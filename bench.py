@@ -244,13 +244,13 @@ def run_ours(args):
   coll = None
   if world > 1:
     from hybridbackend_b200.embedding.sharded import plan_window_bytes
-    sharded_dims = [dim for n in sizes if not hb.embedding.is_small_table(n, world, B)]
+    sharded_dims = [dim for n in sizes if not hb.embedding.is_small_table(n, world, -1)]
     wbytes = plan_window_bytes(world, [B] * len(sharded_dims), sharded_dims, args.capacity_factor)
     coll = hb.distribute.Collective(rank, world, window_bytes=wbytes, device=dev)
   g = torch.Generator(device=dev).manual_seed(1234 + rank)
   tables = []
   for k, n in enumerate(sizes):
-    t = hb.embedding.ShardedEmbeddingWeights(f'emb{k}', n, dim, rank, world, batch_size=B, device=dev)
+    t = hb.embedding.ShardedEmbeddingWeights(f"emb{k}", n, dim, rank, world, batch_size=-1, device=dev)
     t.weight.uniform_(-1e-3, 1e-3, generator=g)
     tables.append(t)
   gl = hb.embedding.GroupLookup(tables, ['mean'] * F, collective=coll, max_nnz=[B] * F,

@@ -96,9 +96,10 @@ struct RadixFirstTraits {  // int64 global id -> uint32 local row, first digit
   using In = int64_t;
   using Out = uint32_t;
   static __device__ __forceinline__ Out conv(In v, const BucketParams& P, const BucketSeg& sg) {
-    if (v < 0) return 0xFFFFFFFFu;
+    if (v == INT64_MIN) return 0xFFFFFFFFu;  // padding entry: skipped silently
+    if (v < 0) return 0xFFFFFFFEu;           // invalid id: skipped, raises the status word
     const uint64_t r = (P.div_shift >= 0) ? ((uint64_t)v >> P.div_shift) : (uint64_t)(v / P.div);
-    return (r >= (uint64_t)sg.key_limit) ? 0xFFFFFFFFu : (uint32_t)r;
+    return (r >= (uint64_t)sg.key_limit) ? 0xFFFFFFFEu : (uint32_t)r;
   }
   static __device__ __forceinline__ int bin(In v, const BucketParams& P, const BucketSeg& sg) {
     return (int)((conv(v, P, sg) >> sg.shift) & (uint32_t)(P.nbins - 1));

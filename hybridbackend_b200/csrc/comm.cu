@@ -413,8 +413,9 @@ int hbAlltoallvN(hbComm* c, int n, const void* const* d_inputs, const int64_t* c
   }
   c->data_calls = call;
   const int half = call & 1;
-  const uint64_t half_bytes = (c->window_bytes / 2) & ~(uint64_t)255;
-  const uint64_t woff = control_bytes();
+  HB_REQUIRE(c->window_bytes > c->reserved_bytes, "hbAlltoallvN: no window space left beside the sharded plan");
+  const uint64_t half_bytes = ((c->window_bytes - c->reserved_bytes) / 2) & ~(uint64_t)255;
+  const uint64_t woff = control_bytes() + c->reserved_bytes;
   PeerPtrs pp = peer_ptrs(c);
   {
     KernelScope ks(HB_K_A2A_TABLES, stream);

@@ -32,6 +32,7 @@ struct Control {
   uint32_t plan_flags[8][kMaxWorld];                // sharded-plan phases (sharded.cu)
   uint32_t done_counter[8];                         // last-CTA-done counters
   int32_t mailbox[2][kMaxWorld * kMaxA2aTensors * kMaxWorld];  // [parity][q][k][r]
+  int32_t plan_mailbox[2][kMaxWorld * kMaxA2aTensors * kMaxWorld];  // sharded plan sizes
   Snapshot snap[kSnapSlots];
 };
 
@@ -42,6 +43,7 @@ constexpr uint64_t kChunkBytes = 16384;
 struct hbComm {
   int rank, world, local;
   size_t window_bytes;   // data window size
+  size_t reserved_bytes; // leading part of the window owned by a sharded plan
   size_t alloc_bytes;
   unsigned char* base;   // local allocation
   unsigned char* peer[hb::kMaxWorld];  // mapped peer allocations (own = base)

@@ -85,9 +85,39 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys_u32(const uint32_t* p) {
   return v;
 }
 
+// Cross-GPU dependency of a kernel: spin until flags[0..n) (epoch-valued words
+// in LOCAL memory, written by peers with st.release.sys) reach `epoch`.
+struct WaitSpec {
+  const uint32_t* flags;
+  uint32_t epoch;
+  int32_t n;
+};
+
+__device__ __forceinline__ void wait_spec(const WaitSpec& w) {
+  if (w.flags != nullptr) {
+    if ((int)threadIdx.x < w.n) {
+      while ((int32_t)(ld_acquire_sys_u32(w.flags + threadIdx.x) - w.epoch) < 0) {
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // sticky device status word bits (hbStatusWord)
 __device__ __forceinline__ void raise_status(int32_t* status, int32_t bit) {
   if (status != nullptr) atomicOr(status, bit);
 }
+
+// ---- internal entry points shared between translation units ----------------
+// lookup.cu: idx32[k] != nullptr -> rows of feature k are addressed by int32
+// indices (stitch of the sharded path) instead of int64 ids; `coherent` uses
+// plain ld.global (data written by peers) instead of ld.global.nc.
+int lookup_forward_run(int n, const hbLookupFeature* feats, const int32_t* const* idx32,
+                       const WaitSpec* wait, bool coherent, int32_t* d_status,
+                       cudaStream_t stream, int kernel_id);
+// sparse_update.cu
+int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* opt, void* ws,
+                      size_t ws_bytes, int32_t* d_status, cudaStream_t stream,
+                      const WaitSpec* wait);
 
 }  // namespace hb

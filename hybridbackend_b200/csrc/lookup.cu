@@ -23,6 +23,7 @@ struct LookupFeat {
   const float* table;
   const int64_t* ids;
   const int64_t* offsets;
+  const int32_t* idx32;   // when set: row index of position p is idx32[p]
   float* out;
   int64_t rows;
   int64_t out_stride;
@@ -37,6 +38,7 @@ struct LookupFeat {
 
 struct LookupParams {
   LookupFeat f[kMaxLookupFeats];
+  WaitSpec wait;
   int32_t* status;
   int32_t nfeats;
   int32_t total_ctas;
@@ -50,6 +52,15 @@ __device__ __forceinline__ int find_feat(const LookupParams& P, int cta) {
   }
   return lo;
 }
+
+template <bool COH>
+__device__ __forceinline__ float4 ld_row4(const float4* p) {
+  if constexpr (COH) return *p;
+  else return ld_nc_f4(p);
+}
+
+// row index of id position p
+__device__ __forceinline__ int64_t row_of(const LookupFeat& F, int64_t p);
 
 __device__ __forceinline__ int64_t local_row(int64_t id, const LookupFeat& F) {
   if (id < 0) return -1;  // never a valid row
@@ -65,9 +76,15 @@ __device__ __forceinline__ float4 f4_div(const float4& a, float c) {
   return make_float4(__fdiv_rn(a.x, c), __fdiv_rn(a.y, c), __fdiv_rn(a.z, c), __fdiv_rn(a.w, c));
 }
 
-template <int V>
+__device__ __forceinline__ int64_t row_of(const LookupFeat& F, int64_t p) {
+  if (F.idx32 != nullptr) return (int64_t)F.idx32[p];
+  return local_row(ld_nc_i64(F.ids + p), F);
+}
+
+template <int V, bool COH>
 __global__ void __launch_bounds__(kLookupThreads)
 lookup_fwd_kernel(const __grid_constant__ LookupParams P) {
+  wait_spec(P.wait);
   const int fi = find_feat(P, blockIdx.x);
   const LookupFeat& F = P.f[fi];
   const int chunk = blockIdx.x - F.cta_begin;
@@ -98,8 +115,7 @@ lookup_fwd_kernel(const __grid_constant__ LookupParams P) {
     for (int u = 0; u < kBagsPerGroup; ++u) {
       const int b = bag0 + u * groups + g;
       ok[u] = b < nbags;
-      const int64_t id = ok[u] ? ld_nc_i64(F.ids + b) : 0;
-      r[u] = local_row(id, F);
+      r[u] = ok[u] ? row_of(F, b) : 0;
       if (ok[u] && (uint64_t)r[u] >= (uint64_t)F.rows) { oob = true; r[u] = -1; }
     }
     float4 val[kBagsPerGroup][V];
@@ -109,7 +125,7 @@ lookup_fwd_kernel(const __grid_constant__ LookupParams P) {
       for (int v = 0; v < V; ++v) {
         val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok[u] && r[u] >= 0 && act[v])
-          val[u][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.table + r[u] * dim + col[v]));
+          val[u][v] = ld_row4<COH>(reinterpret_cast<const float4*>(F.table + r[u] * dim + col[v]));
       }
 #pragma unroll
     for (int u = 0; u < kBagsPerGroup; ++u) {
@@ -138,7 +154,7 @@ lookup_fwd_kernel(const __grid_constant__ LookupParams P) {
         for (int k = 0; k < 4; ++k) {
           r[k] = -1;
           if (p + k < e) {
-            r[k] = local_row(ld_nc_i64(F.ids + p + k), F);
+            r[k] = row_of(F, p + k);
             if ((uint64_t)r[k] >= (uint64_t)F.rows) { oob = true; r[k] = -1; }
           }
         }
@@ -149,7 +165,7 @@ lookup_fwd_kernel(const __grid_constant__ LookupParams P) {
           for (int v = 0; v < V; ++v) {
             x[k][v] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r[k] >= 0 && act[v])
-              x[k][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.table + r[k] * dim + col[v]));
+              x[k][v] = ld_row4<COH>(reinterpret_cast<const float4*>(F.table + r[k] * dim + col[v]));
           }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -191,17 +207,18 @@ static void lookup_shape(int dim, int* log2g, int* v) {
 }
 
 template <int V>
-static int launch_lookup(const LookupParams& P, cudaStream_t stream) {
+static int launch_lookup(const LookupParams& P, cudaStream_t stream, bool coherent, int kid) {
   if (P.total_ctas == 0) return HB_OK;
   {
-    KernelScope ks(HB_K_LOOKUP_FWD, stream);
-    lookup_fwd_kernel<V><<<P.total_ctas, kLookupThreads, 0, stream>>>(P);
+    KernelScope ks(kid, stream);
+    if (coherent) lookup_fwd_kernel<V, true><<<P.total_ctas, kLookupThreads, 0, stream>>>(P);
+    else lookup_fwd_kernel<V, false><<<P.total_ctas, kLookupThreads, 0, stream>>>(P);
   }
   HB_CUDA_OK(cudaGetLastError());
   return HB_OK;
 }
 
-static int validate_feature(int k, const hbLookupFeature& f) {
+static int validate_feature(int k, const hbLookupFeature& f, bool has_idx32) {
   HB_REQUIRE(f.dim >= 4 && f.dim % 4 == 0 && f.dim <= 1024,
              "lookup: feature %d dim %d must be a multiple of 4 in [4,1024]", k, f.dim);
   HB_REQUIRE(f.nbags >= 0 && f.nbags <= INT32_MAX, "lookup: feature %d bad nbags", k);
@@ -212,24 +229,22 @@ static int validate_feature(int k, const hbLookupFeature& f) {
              (long long)f.out_stride);
   HB_REQUIRE(f.combiner >= HB_SUM && f.combiner <= HB_SQRTN, "lookup: feature %d bad combiner", k);
   if (f.nbags > 0) {
-    HB_REQUIRE(f.table && f.ids && f.out, "lookup: feature %d null pointer", k);
+    HB_REQUIRE(f.table && (f.ids || has_idx32) && f.out, "lookup: feature %d null pointer", k);
     HB_REQUIRE(((uintptr_t)f.table & 15) == 0 && ((uintptr_t)f.out & 15) == 0,
                "lookup: feature %d table/out must be 16-byte aligned", k);
   }
   return HB_OK;
 }
 
-}  // namespace hb
-
-extern "C" int hbGroupLookupForward(int n, const hbLookupFeature* feats, int32_t* d_status,
-                                    hbStream stream_) {
-  using namespace hb;
-  cudaStream_t stream = (cudaStream_t)stream_;
+int lookup_forward_run(int n, const hbLookupFeature* feats, const int32_t* const* idx32,
+                       const WaitSpec* wait, bool coherent, int32_t* d_status,
+                       cudaStream_t stream, int kernel_id) {
   HB_REQUIRE(n >= 1 && feats != nullptr, "hbGroupLookupForward: need n >= 1 features");
   for (int k = 0; k < n; ++k) {
-    int rc = validate_feature(k, feats[k]);
+    int rc = validate_feature(k, feats[k], idx32 != nullptr && idx32[k] != nullptr);
     if (rc != HB_OK) return rc;
   }
+  bool waited = false;
   // one launch per distinct V (1 for every dim <= 128), chunks of kMaxLookupFeats
   for (int V = 1; V <= 8; V <<= 1) {
     LookupParams P;
@@ -239,11 +254,14 @@ extern "C" int hbGroupLookupForward(int n, const hbLookupFeature* feats, int32_t
     auto flush = [&]() -> int {
       int rc = HB_OK;
       if (P.nfeats > 0) {
+        // only the first launch has to wait: later ones are stream-ordered after it
+        P.wait = (wait != nullptr && !waited) ? *wait : WaitSpec{nullptr, 0, 0};
+        waited = true;
         switch (V) {
-          case 1: rc = launch_lookup<1>(P, stream); break;
-          case 2: rc = launch_lookup<2>(P, stream); break;
-          case 4: rc = launch_lookup<4>(P, stream); break;
-          default: rc = launch_lookup<8>(P, stream); break;
+          case 1: rc = launch_lookup<1>(P, stream, coherent, kernel_id); break;
+          case 2: rc = launch_lookup<2>(P, stream, coherent, kernel_id); break;
+          case 4: rc = launch_lookup<4>(P, stream, coherent, kernel_id); break;
+          default: rc = launch_lookup<8>(P, stream, coherent, kernel_id); break;
         }
       }
       P.nfeats = 0;
@@ -257,6 +275,7 @@ extern "C" int hbGroupLookupForward(int n, const hbLookupFeature* feats, int32_t
       if (v != V || f.nbags == 0) continue;
       LookupFeat& F = P.f[P.nfeats];
       F.table = f.table; F.ids = f.ids; F.offsets = f.offsets; F.out = f.out;
+      F.idx32 = idx32 ? idx32[k] : nullptr;
       F.rows = f.rows; F.out_stride = f.out_stride; F.id_div = f.id_div;
       F.nbags = (int32_t)f.nbags; F.dim = f.dim; F.combiner = f.combiner;
       F.div_shift = ((f.id_div & (f.id_div - 1)) == 0) ? ilog2_ceil((int)f.id_div) : -1;
@@ -276,6 +295,14 @@ extern "C" int hbGroupLookupForward(int n, const hbLookupFeature* feats, int32_t
     if (rc != HB_OK) return rc;
   }
   return HB_OK;
+}
+
+}  // namespace hb
+
+extern "C" int hbGroupLookupForward(int n, const hbLookupFeature* feats, int32_t* d_status,
+                                    hbStream stream_) {
+  return hb::lookup_forward_run(n, feats, nullptr, nullptr, false, d_status,
+                                (cudaStream_t)stream_, HB_K_LOOKUP_FWD);
 }
 
 extern "C" int hbGroupLookupForwardHost(int n, const hbLookupFeature* feats, const void* h_in_block,

@@ -51,6 +51,7 @@ struct UpdFeat {
 
 struct UpdParams {
   UpdFeat f[kMaxUpdFeats];
+  WaitSpec wait;
   int32_t* status;
   int32_t nfeats;
   int32_t total_ctas;
@@ -117,7 +118,8 @@ template <int V>
 __device__ __forceinline__ bool apply_row(const UpdParams& P, const UpdFeat& F, uint32_t key,
                                           const float4 (&acc)[V], const int (&col)[V],
                                           const bool (&act)[V]) {
-  if ((uint64_t)key >= (uint64_t)F.rows) return false;  // out-of-range id (sentinel)
+  if (key == 0xFFFFFFFFu) return true;                  // padding entry (sharded path)
+  if ((uint64_t)key >= (uint64_t)F.rows) return false;  // out-of-range id
   const int64_t base = (int64_t)key * F.dim;
 #pragma unroll
   for (int v = 0; v < V; ++v)
@@ -132,6 +134,7 @@ template <int V, int C>
 __global__ void __launch_bounds__(kUpdThreads)
 sparse_update_kernel(const __grid_constant__ UpdParams P) {
   extern __shared__ __align__(16) unsigned char s_raw[];
+  wait_spec(P.wait);
   const int fi = find_upd_feat(P, blockIdx.x);
   const UpdFeat& F = P.f[fi];
   const int st = blockIdx.x - F.cta_begin;
@@ -472,10 +475,11 @@ static int validate_upd(int k, const hbUpdateFeature& f, const hbOptimizer* opt)
   return HB_OK;
 }
 
-// Sort (row, bag) pairs of every feature and run the fused update.  `ids_div`
+// Sort (row, bag) pairs of every feature and run the fused update.  `id_div`
 // is shared by the features of one call (1 locally, W on a row-interleaved shard).
 int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* opt, void* ws,
-                      size_t ws_bytes, int32_t* d_status, cudaStream_t stream) {
+                      size_t ws_bytes, int32_t* d_status, cudaStream_t stream,
+                      const WaitSpec* wait) {
   HB_REQUIRE(n >= 1 && feats && opt, "update: bad arguments");
   HB_REQUIRE(opt->kind >= HB_OPT_SGD && opt->kind <= HB_OPT_LAZY_ADAM, "update: bad optimizer kind %d", opt->kind);
   for (int k = 0; k < n; ++k) {
@@ -584,6 +588,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
     // 3./4. fused update + fix-up, one launch per V
     for (int V = 1; V <= 8; V <<= 1) {
       UpdParams U;
+      U.wait = wait ? *wait : WaitSpec{nullptr, 0, 0};
       U.status = d_status;
       U.nfeats = 0;
       U.total_ctas = 0;
@@ -678,7 +683,7 @@ int hbGroupLookupBackwardUpdate(int n, const hbUpdateFeature* feats, const hbOpt
                                 void* d_workspace, size_t workspace_bytes, int32_t* d_status,
                                 hbStream stream) {
   return hb::sparse_update_run(n, feats, opt, d_workspace, workspace_bytes, d_status,
-                               (cudaStream_t)stream);
+                               (cudaStream_t)stream, nullptr);
 }
 
 }  // extern "C"

@@ -92,7 +92,7 @@ class GroupLookup:
   """
 
   def __init__(self, tables, combiners=None, collective=None, max_nnz=None,
-               capacity_factor=None):
+               capacity_factor=None, sync_replicated=True):
     self.tables = list(tables)
     self.n = len(self.tables)
     if self.n < 1:
@@ -105,6 +105,7 @@ class GroupLookup:
     self.out_dim = self.col_offsets[-1]
     self.device = _weight_of(self.tables[0]).device
     self.collective = collective
+    self.sync_replicated = sync_replicated
     self._saved = None
     self._sharded = None
     world = collective.world_size if collective is not None else 1
@@ -215,15 +216,23 @@ class GroupLookup:
       if self.local_idx:
         m = len(self.local_idx)
         feats = (_lib.hbUpdateFeature * m)()
+        sync = (self.collective is not None and self.collective.world_size > 1 and
+                self.sync_replicated)
+        keep = []
         for j, k in enumerate(self.local_idx):
           t = self.tables[k]
           w = _weight_of(t)
           slots = self._slots(k, optimizer)
+          ids_k, off_k, g_k, g_stride, nb = ids[k], offsets[k], grad[:, self.col_offsets[k]:], grad.stride(0), B
+          if sync:
+            ids_k, g_k, nb = self._allgather_replicated(k, ids[k], offsets[k], grad)
+            off_k, g_stride = None, g_k.stride(0)
+            keep.append((ids_k, g_k))
           feats[j] = _lib.hbUpdateFeature(
               w.data_ptr(), slots[0].data_ptr() if len(slots) > 0 else None,
               slots[1].data_ptr() if len(slots) > 1 else None, w.shape[0],
-              ids[k].data_ptr(), offsets[k].data_ptr() if offsets[k] is not None else None,
-              B, ids[k].numel(), grad[:, self.col_offsets[k]:].data_ptr(), grad.stride(0),
+              ids_k.data_ptr(), off_k.data_ptr() if off_k is not None else None,
+              nb, ids_k.numel(), g_k.data_ptr(), g_stride,
               w.shape[1], _lib.COMBINER[self.combiners[k]], 1)
         need = _lib.C.c_size_t(0)
         _lib.check(L.hbGroupSparseUpdateWorkspaceBytes(m, feats, _lib.C.byref(need)),
@@ -238,6 +247,26 @@ class GroupLookup:
                                       optimizer, desc, st)
     if check:
       _util.check_status(self.device)
+
+  def _allgather_replicated(self, k, ids_k, off_k, grad):
+    """Replicated ("small") tables: every rank applies the gradients of ALL ranks
+    so replicas stay identical -- the reference all-gathers the IndexedSlices
+    values+indices of replicated sparse gradients (training/gradient.py:163-177).
+    NCCL all-gather via torch.distributed: the dense/replicated path keeps NCCL
+    (SURVEY.md section 2 row 4)."""
+    import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+    if off_k is not None:
+      raise NotImplementedError(
+          'gradient all-gather of a replicated table needs one id per bag; give multi-id '
+          'bags to sharded tables or pass sync_replicated=False')
+    W = self.collective.world_size
+    d = self.dims[k]
+    g_local = grad[:, self.col_offsets[k]:self.col_offsets[k] + d].contiguous()
+    all_ids = torch.empty(W * ids_k.numel(), dtype=torch.int64, device=self.device)
+    all_g = torch.empty(W * g_local.shape[0], d, dtype=torch.float32, device=self.device)
+    dist.all_gather_into_tensor(all_ids, ids_k.contiguous())
+    dist.all_gather_into_tensor(all_g, g_local)
+    return all_ids, all_g, all_ids.numel()
 
   def _slots(self, k, optimizer):
     t = self.tables[k]

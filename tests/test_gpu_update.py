@@ -28,7 +28,8 @@ def _oracle_step(oracle, opt, tables, slots, feats, grad, cols, combiner, step):
                                     1e-8, step)
 
 
-def _run(hb, oracle, opt, combiner, rows_list, D, B, steps=2, one_hot=False, zipf=False, seed=0):
+def _run(hb, oracle, opt, combiner, rows_list, D, B, steps=2, one_hot=False, zipf=False, seed=0,
+         rtol=RTOL):
   rng = np.random.RandomState(seed)
   n = len(rows_list)
   tables = [rng.uniform(-1e-1, 1e-1, (r, D)).astype(np.float32) for r in rows_list]
@@ -56,9 +57,9 @@ def _run(hb, oracle, opt, combiner, rows_list, D, B, steps=2, one_hot=False, zip
     _oracle_step(oracle, opt, tables, slots, feats, grad, cols, combiner, step)
   for k in range(n):
     got = dev_tables[k].cpu().numpy()
-    np.testing.assert_allclose(got, tables[k], rtol=RTOL, atol=1e-6, err_msg=f'table {k}')
+    np.testing.assert_allclose(got, tables[k], rtol=rtol, atol=1e-6, err_msg=f'table {k}')
     for s_dev, s_ref in zip(gl.slots(k), slots[k]):
-      np.testing.assert_allclose(s_dev.cpu().numpy(), s_ref, rtol=RTOL, atol=1e-6)
+      np.testing.assert_allclose(s_dev.cpu().numpy(), s_ref, rtol=rtol, atol=1e-6)
   return dev_tables, tables
 
 
@@ -77,7 +78,10 @@ def test_adagrad_one_hot_no_dups_bit_exact(hb, oracle):
 def test_adagrad_hot_rows_tiny_tables(hb, oracle):
   # Criteo has tables of 3..155 rows: thousands of duplicates per row, rows span
   # many tiles and super-tiles (exercises the in-CTA combine and the fix-up kernel)
-  _run(hb, oracle, 'adagrad', 'mean', [3, 4, 10, 63, 155, 976], 32, 20000, one_hot=True)
+  # a row sums ~7000 gradients: the oracle adds them strictly left to right, the
+  # kernel in a fixed tile tree -- both are valid fp32 sums of the same terms and
+  # differ by O(sqrt(n)) ulp, hence the wider tolerance for THIS case only
+  _run(hb, oracle, 'adagrad', 'mean', [3, 4, 10, 63, 155, 976], 32, 20000, one_hot=True, rtol=2e-4)
 
 
 def test_adagrad_zipf(hb, oracle):
