@@ -51,7 +51,7 @@ def parse_args():
   p.add_argument('--cpu-sample-steps', type=int, default=3)
   p.add_argument('--no-cpu-baseline', action='store_true')
   p.add_argument('--no-e2e', action='store_true')
-  p.add_argument('--capacity-factor', type=float, default=2.0)
+  p.add_argument('--capacity-factor', type=float, default=0.0, help='0: world size (always safe)')
   return p.parse_args()
 
 
@@ -239,6 +239,8 @@ def run_ours(args):
   dim = args.dim or (32 if world == 1 else 64)
   sizes = table_sizes(args)
   F, B = len(sizes), args.batch
+  if args.capacity_factor <= 0:
+    args.capacity_factor = float(world)
 
   # ---- tables (row-sharded where the reference shards them) ----------------------
   coll = None

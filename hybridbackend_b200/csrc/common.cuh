@@ -118,6 +118,6 @@ int lookup_forward_run(int n, const hbLookupFeature* feats, const int32_t* const
 // sparse_update.cu
 int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* opt, void* ws,
                       size_t ws_bytes, int32_t* d_status, cudaStream_t stream,
-                      const WaitSpec* wait);
+                      const WaitSpec* wait, const int32_t* const* n_dev);
 
 }  // namespace hb

@@ -61,8 +61,8 @@ KernelScope::~KernelScope() {
 }
 
 static const char* kKernelNames[HB_K_COUNT] = {
-    "", "partition_count", "partition_scan", "partition_scatter", "sort_count", "sort_scan",
-    "sort_scatter", "bag_of_position", "lookup_fwd", "sparse_update", "sparse_update_fixup",
+    "", "partition_hist", "partition_pass", "", "sort_hist", "sort_pass",
+    "", "bag_of_position", "lookup_fwd", "sparse_update", "sparse_update_fixup",
     "cast_n", "cache_lookup", "barrier", "a2a_sizes", "a2a_tables", "a2a_push", "a2a_copyout",
     "sharded_exchange", "sharded_push_ids", "sharded_owner_gather", "sharded_stitch_pool",
     "sharded_push_grads", "sharded_pad"};

@@ -40,7 +40,7 @@ struct ShFeatMeta {
   int32_t recv_base[kMaxWorld + 1];   // as owner: start of source q's segment (clamped to cap)
   int32_t src_bucket_off[kMaxWorld];  // as owner: start of bucket `me` in q's partitioned order
   int32_t recv_total;                 // unclamped number of ids addressed to me
-  int32_t cap;                        // owner-side capacity (ids)
+  int32_t recv_clamped;               // min(recv_total, cap): entries actually received
 };
 
 struct ShFeat {
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) sh_exchange_kernel(const __grid_constant_
     }
     m.recv_total = acc;
     for (int q = W; q <= kMaxWorld; ++q) m.recv_base[q] = acc < cap ? acc : cap;
-    m.cap = cap;
+    m.recv_clamped = acc < cap ? acc : cap;
     if (acc > cap) raise_status(P.status, HB_STATUS_WINDOW_OVERFLOW);
     P.meta[f] = m;
   }
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) sh_owner_gather_kernel(const __grid_const
   const int dim = F.dim;
   const int chunk = blockIdx.x - F.cta_begin;
   const int p0 = chunk * groups * kShRowsPerGroup;
-  const int total = m.recv_total < F.cap ? m.recv_total : F.cap;
+  const int total = m.recv_clamped;
   int64_t* ids_in = reinterpret_cast<int64_t*>(win(P, P.me) + F.ids_in_off[P.parity]);
   bool oob = false;
   int col[V];
@@ -252,8 +252,6 @@ __global__ void __launch_bounds__(256) sh_owner_gather_kernel(const __grid_const
       while (qq + 1 < P.world && m.recv_base[qq + 1] <= p) ++qq;
       q[u] = qq;
       dstrow[u] = m.src_bucket_off[qq] + (p - m.recv_base[qq]);
-    } else if (p < F.cap && l == 0) {
-      ids_in[p] = INT64_MIN;  // padding for the backward sort
     }
   }
   float4 val[kShRowsPerGroup][V];
@@ -784,7 +782,10 @@ int hbShardedLookupBackwardUpdate(hbShardedPlan* pl, const hbShardedFeature* fea
     }
     Control* mine = reinterpret_cast<Control*>(c->base);
     WaitSpec w{&mine->plan_flags[3][0], pl->step, W};
-    rc = sparse_update_run(n, uf.data(), opt, pl->upd_ws, pl->upd_ws_bytes, d_status, stream, &w);
+    std::vector<const int32_t*> ndev(n);
+    for (int k = 0; k < n; ++k) ndev[k] = &pl->meta[k].recv_clamped;
+    rc = sparse_update_run(n, uf.data(), opt, pl->upd_ws, pl->upd_ws_bytes, d_status, stream, &w,
+                           ndev.data());
     if (rc != HB_OK) return rc;
   }
   return HB_OK;

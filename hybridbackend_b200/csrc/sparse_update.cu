@@ -39,6 +39,7 @@ struct UpdFeat {
   float* st_part;           // [nst][2][dim] partial sums of open runs
   uint32_t* st_key;         // [nst][2]
   int32_t* st_flag;         // [nst]
+  const int32_t* n_dev;     // may be nullptr: device-side number of entries (<= n)
   int64_t rows;
   int64_t grad_stride;
   int32_t n;
@@ -76,28 +77,25 @@ __device__ __forceinline__ float4 f4_add_rn(const float4& a, const float4& b) {
                      __fadd_rn(a.w, b.w));
 }
 
-// One optimizer step on 4 consecutive elements of a row.
-__device__ __forceinline__ void opt_apply4(const UpdParams& P, float* w, float* s0, float* s1,
-                                           const float4& g) {
-  float4 wv = *reinterpret_cast<float4*>(w);
+// One optimizer step on 4 consecutive elements of a row (values in registers).
+template <int OPT>
+__device__ __forceinline__ void opt_step4(const UpdParams& P, float4& wv, float4& s0v, float4& s1v,
+                                          const float4& g) {
   const float gg[4] = {g.x, g.y, g.z, g.w};
   float ww[4] = {wv.x, wv.y, wv.z, wv.w};
-  if (P.opt == HB_OPT_ADAGRAD) {
+  if constexpr (OPT == HB_OPT_ADAGRAD) {
     // SparseApplyAdagrad: accum += g*g ; var -= lr*g/sqrt(accum)
-    float4 av = *reinterpret_cast<float4*>(s0);
-    float aa[4] = {av.x, av.y, av.z, av.w};
+    float aa[4] = {s0v.x, s0v.y, s0v.z, s0v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       aa[i] = __fadd_rn(aa[i], __fmul_rn(gg[i], gg[i]));
       ww[i] = __fsub_rn(ww[i], __fdiv_rn(__fmul_rn(P.lr, gg[i]), __fsqrt_rn(aa[i])));
     }
-    *reinterpret_cast<float4*>(s0) = make_float4(aa[0], aa[1], aa[2], aa[3]);
-  } else if (P.opt == HB_OPT_LAZY_ADAM) {
+    s0v = make_float4(aa[0], aa[1], aa[2], aa[3]);
+  } else if constexpr (OPT == HB_OPT_LAZY_ADAM) {
     // LazyAdam: m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; var -= lr_t*m/(sqrt(v)+eps)
-    float4 mv = *reinterpret_cast<float4*>(s0);
-    float4 vv = *reinterpret_cast<float4*>(s1);
-    float mm[4] = {mv.x, mv.y, mv.z, mv.w};
-    float v2[4] = {vv.x, vv.y, vv.z, vv.w};
+    float mm[4] = {s0v.x, s0v.y, s0v.z, s0v.w};
+    float v2[4] = {s1v.x, s1v.y, s1v.z, s1v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       mm[i] = __fadd_rn(__fmul_rn(P.beta1, mm[i]), __fmul_rn(P.omb1, gg[i]));
@@ -105,33 +103,70 @@ __device__ __forceinline__ void opt_apply4(const UpdParams& P, float* w, float* 
       ww[i] = __fsub_rn(ww[i], __fdiv_rn(__fmul_rn(P.lr, mm[i]),
                                          __fadd_rn(__fsqrt_rn(v2[i]), P.eps)));
     }
-    *reinterpret_cast<float4*>(s0) = make_float4(mm[0], mm[1], mm[2], mm[3]);
-    *reinterpret_cast<float4*>(s1) = make_float4(v2[0], v2[1], v2[2], v2[3]);
+    s0v = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    s1v = make_float4(v2[0], v2[1], v2[2], v2[3]);
   } else {  // SGD
 #pragma unroll
     for (int i = 0; i < 4; ++i) ww[i] = __fsub_rn(ww[i], __fmul_rn(P.lr, gg[i]));
   }
-  *reinterpret_cast<float4*>(w) = make_float4(ww[0], ww[1], ww[2], ww[3]);
+  wv = make_float4(ww[0], ww[1], ww[2], ww[3]);
 }
 
-template <int V>
+// Apply the optimizer to up to N rows at once: all row loads (table + slots) are
+// issued before the first use, so N*(1+slots) 128-bit loads are in flight per lane.
+template <int V, int N, int OPT>
+__device__ __forceinline__ bool apply_rows(const UpdParams& P, const UpdFeat& F, unsigned mask,
+                                           const uint32_t (&key)[N], const float4 (&g)[N][V],
+                                           const int (&col)[V], const bool (&act)[V]) {
+  bool all_ok = true;
+  bool ok[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    ok[i] = (mask >> i) & 1u;
+    if (ok[i] && key[i] == 0xFFFFFFFFu) ok[i] = false;  // padding entry (sharded path)
+    if (ok[i] && (uint64_t)key[i] >= (uint64_t)F.rows) { ok[i] = false; all_ok = false; }
+  }
+  float4 w[N][V], s0[N][V], s1[N][V];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      w[i][v] = s0[i][v] = s1[i][v] = f4_zero();
+      if (ok[i] && act[v]) {
+        const int64_t o = (int64_t)key[i] * F.dim + col[v];
+        w[i][v] = *reinterpret_cast<const float4*>(F.table + o);
+        if constexpr (OPT != HB_OPT_SGD) s0[i][v] = *reinterpret_cast<const float4*>(F.slot0 + o);
+        if constexpr (OPT == HB_OPT_LAZY_ADAM) s1[i][v] = *reinterpret_cast<const float4*>(F.slot1 + o);
+      }
+    }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      if (ok[i] && act[v]) {
+        const int64_t o = (int64_t)key[i] * F.dim + col[v];
+        opt_step4<OPT>(P, w[i][v], s0[i][v], s1[i][v], g[i][v]);
+        *reinterpret_cast<float4*>(F.table + o) = w[i][v];
+        if constexpr (OPT != HB_OPT_SGD) *reinterpret_cast<float4*>(F.slot0 + o) = s0[i][v];
+        if constexpr (OPT == HB_OPT_LAZY_ADAM) *reinterpret_cast<float4*>(F.slot1 + o) = s1[i][v];
+      }
+  return all_ok;
+}
+
+template <int V, int OPT>
 __device__ __forceinline__ bool apply_row(const UpdParams& P, const UpdFeat& F, uint32_t key,
                                           const float4 (&acc)[V], const int (&col)[V],
                                           const bool (&act)[V]) {
-  if (key == 0xFFFFFFFFu) return true;                  // padding entry (sharded path)
-  if ((uint64_t)key >= (uint64_t)F.rows) return false;  // out-of-range id
-  const int64_t base = (int64_t)key * F.dim;
+  const uint32_t k1[1] = {key};
+  float4 g1[1][V];
 #pragma unroll
-  for (int v = 0; v < V; ++v)
-    if (act[v])
-      opt_apply4(P, F.table + base + col[v], F.slot0 ? F.slot0 + base + col[v] : nullptr,
-                 F.slot1 ? F.slot1 + base + col[v] : nullptr, acc[v]);
-  return true;
+  for (int v = 0; v < V; ++v) g1[0][v] = acc[v];
+  return apply_rows<V, 1, OPT>(P, F, 1u, k1, g1, col, act);
 }
 
 // smem per CTA: groups * (2*V*G float4 partials + 2 keys + 1 flag)
-template <int V, int C>
-__global__ void __launch_bounds__(kUpdThreads)
+template <int V, int C, int OPT>
+__global__ void __launch_bounds__(kUpdThreads, (V == 1 ? 3 : 1))
 sparse_update_kernel(const __grid_constant__ UpdParams P) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   wait_spec(P.wait);
@@ -144,7 +179,8 @@ sparse_update_kernel(const __grid_constant__ UpdParams P) {
   const int g = threadIdx.x >> log2g;
   const int l = threadIdx.x & (G - 1);
   const int dim = F.dim;
-  const int n = F.n;
+  int n = F.n;
+  if (F.n_dev != nullptr) { const int d = *F.n_dev; n = d < 0 ? 0 : (d < n ? d : n); }
   // smem carve-up
   float4* s_part = reinterpret_cast<float4*>(s_raw);                  // [groups][2][V][G]
   uint32_t* s_key = reinterpret_cast<uint32_t*>(s_part + (size_t)groups * 2 * V * G);  // [groups][2]
@@ -164,89 +200,104 @@ sparse_update_kernel(const __grid_constant__ UpdParams P) {
   int flag = 0;
 
   if (cnt > 0) {
-    uint32_t k[C];
-    int32_t b[C];
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-      k[j] = 0xFFFFFFFFu;
-      b[j] = 0;
-      if (j < cnt) { k[j] = F.keys[e0 + j]; b[j] = F.bags[e0 + j]; }
-    }
     const bool has_prev = e0 > 0;
     const bool has_next = e0 + cnt < n;
     const uint32_t pk = has_prev ? F.keys[e0 - 1] : 0u;
     const uint32_t nk = has_next ? F.keys[e0 + cnt] : 0u;
-    // bag scale (mean: 1/count, sqrtn: 1/sqrt(count)) -- division as the oracle
-    float sc[C];
+    const uint32_t k_first = F.keys[e0];
+    const bool first_open_left = has_prev && pk == k_first;
+    const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
+    bool seen_tail = false;
+    float4 carry[V];
 #pragma unroll
-    for (int j = 0; j < C; ++j) {
-      sc[j] = 1.0f;
-      if (j < cnt && F.offsets != nullptr && F.combiner != HB_SUM) {
-        const int64_t c = F.offsets[b[j] + 1] - F.offsets[b[j]];
-        sc[j] = (F.combiner == HB_MEAN) ? (float)c : __fsqrt_rn((float)c);
-      }
-    }
-    float4 gv[C][V];
-#pragma unroll
-    for (int j = 0; j < C; ++j)
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        gv[j][v] = f4_zero();
-        if (j < cnt && act[v])
-          gv[j][v] = ld_nc_f4(reinterpret_cast<const float4*>(
-              F.grad + (int64_t)b[j] * F.grad_stride + col[v]));
-      }
-    if (F.combiner != HB_SUM && F.offsets != nullptr) {
-#pragma unroll
-      for (int j = 0; j < C; ++j)
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-          gv[j][v] = make_float4(__fdiv_rn(gv[j][v].x, sc[j]), __fdiv_rn(gv[j][v].y, sc[j]),
-                                 __fdiv_rn(gv[j][v].z, sc[j]), __fdiv_rn(gv[j][v].w, sc[j]));
-    }
-
-    // walk the tile run by run
-    float4 acc[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = f4_zero();
-    uint32_t run_key = k[0];
-    bool open_left = has_prev && pk == k[0];
+    for (int v = 0; v < V; ++v) carry[v] = f4_zero();
     float4* my_part = s_part + (size_t)g * 2 * V * G;
+    constexpr int SB = (C < 4) ? C : 4;  // entries whose loads are batched
+#pragma unroll 1
+    for (int j0 = 0; j0 < cnt; j0 += SB) {
+      // keys of the sub-batch and its two neighbours; bags
+      uint32_t k[SB];
+      int32_t bg[SB];
 #pragma unroll
-    for (int j = 0; j < C; ++j) {
-      if (j < cnt) {
-        if (j > 0 && k[j] != run_key) {
-          // run [.., j) closed on the right
-          if (!open_left) {
-            if (!apply_row<V>(P, F, run_key, acc, col, act)) oob = true;
-          } else {
-#pragma unroll
-            for (int v = 0; v < V; ++v) my_part[(0 * V + v) * G + l] = acc[v];
-            if (l == 0) s_key[g * 2 + 0] = run_key;
-            flag |= kFirstOpen;
-          }
-#pragma unroll
-          for (int v = 0; v < V; ++v) acc[v] = f4_zero();
-          run_key = k[j];
-          open_left = false;
-        }
-#pragma unroll
-        for (int v = 0; v < V; ++v) acc[v] = f4_add_rn(acc[v], gv[j][v]);
+      for (int i = 0; i < SB; ++i) {
+        k[i] = 0xFFFFFFFFu;
+        bg[i] = 0;
+        if (j0 + i < cnt) { k[i] = F.keys[e0 + j0 + i]; bg[i] = F.bags[e0 + j0 + i]; }
       }
-    }
-    const bool open_right = has_next && nk == run_key;
-    if (!open_left && !open_right) {
-      if (!apply_row<V>(P, F, run_key, acc, col, act)) oob = true;
-    } else if (open_left) {
+      const uint32_t k_before = (j0 > 0) ? F.keys[e0 + j0 - 1] : 0u;
+      const uint32_t k_after = (j0 + SB < cnt) ? F.keys[e0 + j0 + SB] : 0u;
+      // bag scale (mean: count, sqrtn: sqrt(count)) -- divided as the oracle does
+      float sc[SB];
 #pragma unroll
-      for (int v = 0; v < V; ++v) my_part[(0 * V + v) * G + l] = acc[v];
-      if (l == 0) s_key[g * 2 + 0] = run_key;
-      flag |= kFirstOpen | (open_right ? kBoth : 0);
-    } else {
+      for (int i = 0; i < SB; ++i) {
+        sc[i] = 1.0f;
+        if (scaled && j0 + i < cnt) {
+          const int64_t c = F.offsets[bg[i] + 1] - F.offsets[bg[i]];
+          sc[i] = (F.combiner == HB_MEAN) ? (float)c : __fsqrt_rn((float)c);
+        }
+      }
+      float4 gv[SB][V];
 #pragma unroll
-      for (int v = 0; v < V; ++v) my_part[(1 * V + v) * G + l] = acc[v];
-      if (l == 0) s_key[g * 2 + 1] = run_key;
-      flag |= kLastOpen;
+      for (int i = 0; i < SB; ++i)
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          gv[i][v] = f4_zero();
+          if (j0 + i < cnt && act[v])
+            gv[i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
+                F.grad + (int64_t)bg[i] * F.grad_stride + col[v]));
+        }
+      if (scaled) {
+#pragma unroll
+        for (int i = 0; i < SB; ++i)
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            gv[i][v] = make_float4(__fdiv_rn(gv[i][v].x, sc[i]), __fdiv_rn(gv[i][v].y, sc[i]),
+                                   __fdiv_rn(gv[i][v].z, sc[i]), __fdiv_rn(gv[i][v].w, sc[i]));
+      }
+      // segmented inclusive sums, in position order
+#pragma unroll
+      for (int i = 0; i < SB; ++i) {
+        if (j0 + i < cnt) {
+          const bool head = (i == 0) ? (j0 == 0 || k[0] != k_before) : (k[i] != k[i - 1]);
+          if (!head) {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+              gv[i][v] = f4_add_rn(i == 0 ? carry[v] : gv[i > 0 ? i - 1 : 0][v], gv[i][v]);
+          }
+        }
+      }
+      // classify run ends
+      unsigned apply_mask = 0;
+#pragma unroll
+      for (int i = 0; i < SB; ++i) {
+        const int j = j0 + i;
+        if (j < cnt) {
+          const bool last = (j == cnt - 1);
+          const uint32_t knext = (i + 1 < SB) ? k[i + 1 < SB ? i + 1 : i] : k_after;
+          const bool tail = last || (k[i] != knext);
+          if (tail) {
+            const bool ol = first_open_left && !seen_tail;
+            const bool orr = last && has_next && nk == k[i];
+            if (!ol && !orr) {
+              apply_mask |= 1u << i;
+            } else if (ol) {
+#pragma unroll
+              for (int v = 0; v < V; ++v) my_part[(0 * V + v) * G + l] = gv[i][v];
+              if (l == 0) s_key[g * 2 + 0] = k[i];
+              flag |= kFirstOpen | (orr ? kBoth : 0);
+            } else {
+#pragma unroll
+              for (int v = 0; v < V; ++v) my_part[(1 * V + v) * G + l] = gv[i][v];
+              if (l == 0) s_key[g * 2 + 1] = k[i];
+              flag |= kLastOpen;
+            }
+            seen_tail = true;
+          }
+        }
+      }
+      if (!apply_rows<V, SB, OPT>(P, F, apply_mask, k, gv, col, act)) oob = true;
+#pragma unroll
+      for (int v = 0; v < V; ++v) carry[v] = gv[SB - 1][v];
     }
   }
   __shared__ int s_stflag;
@@ -295,7 +346,7 @@ sparse_update_kernel(const __grid_constant__ UpdParams P) {
       ++t;
     }
     if (closed) {
-      if (!apply_row<V>(P, F, key, acc, col, act)) oob = true;
+      if (!apply_row<V, OPT>(P, F, key, acc, col, act)) oob = true;
     } else {
       // still open at the end of the super-tile
 #pragma unroll
@@ -314,7 +365,9 @@ sparse_update_kernel(const __grid_constant__ UpdParams P) {
 }
 
 // Finish rows that span super-tiles: group per super-tile that STARTS a chain.
-template <int V>
+// The chain is walked 8 super-tiles at a time: flags and partial sums of the
+// next 8 are loaded speculatively in one round trip, then added in order.
+template <int V, int OPT>
 __global__ void __launch_bounds__(kUpdThreads)
 sparse_update_fixup_kernel(const __grid_constant__ UpdParams P) {
   const int fi = find_upd_feat(P, blockIdx.x);
@@ -341,19 +394,36 @@ sparse_update_fixup_kernel(const __grid_constant__ UpdParams P) {
     acc[v] = act[v] ? *reinterpret_cast<const float4*>(F.st_part + ((size_t)st * 2 + 1) * dim + col[v])
                     : f4_zero();
   const uint32_t key = F.st_key[(size_t)st * 2 + 1];
+  constexpr int kAhead = 8;
   int t = st + 1;
-  while (t < F.nst) {
-    const int fl = F.st_flag[t];
-    if (!(fl & kFirstOpen)) break;
+  bool done = false;
+  while (!done && t < F.nst) {
+    int fl[kAhead];
+    float4 x[kAhead][V];
 #pragma unroll
-    for (int v = 0; v < V; ++v)
-      if (act[v])
-        acc[v] = f4_add_rn(acc[v], *reinterpret_cast<const float4*>(
-                                       F.st_part + ((size_t)t * 2 + 0) * dim + col[v]));
-    if (!(fl & kBoth)) break;
-    ++t;
+    for (int u = 0; u < kAhead; ++u) {
+      fl[u] = (t + u < F.nst) ? F.st_flag[t + u] : 0;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        x[u][v] = (t + u < F.nst && act[v])
+                      ? *reinterpret_cast<const float4*>(F.st_part + ((size_t)(t + u) * 2 + 0) * dim + col[v])
+                      : f4_zero();
+    }
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) {
+      if (!done) {
+        if (!(fl[u] & kFirstOpen)) {
+          done = true;
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = f4_add_rn(acc[v], x[u][v]);
+          if (!(fl[u] & kBoth)) done = true;
+        }
+      }
+    }
+    t += kAhead;
   }
-  if (!apply_row<V>(P, F, key, acc, col, act)) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
+  if (!apply_row<V, OPT>(P, F, key, acc, col, act)) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
 }
 
 // bag index of every id position, for CSR features (thread per bag).
@@ -434,21 +504,33 @@ static UpdLayout upd_layout(const hbUpdateFeature& f, size_t base) {
   return L;
 }
 
-template <int V, int C>
-static int launch_update(const UpdParams& P, int log2g_max, cudaStream_t stream) {
-  (void)log2g_max;
-  if (P.total_ctas == 0) return HB_OK;
+template <int V, int C, int OPT>
+static int launch_update_opt(const UpdParams& P, const UpdParams& X, cudaStream_t stream) {
   // smem: groups*(2*V*G*16 + 12) with groups*G == 256
   const size_t smem = (size_t)2 * V * kUpdThreads * 16 + (size_t)kUpdThreads * 12;
   if (smem > 48 * 1024)
-    HB_CUDA_OK(cudaFuncSetAttribute(sparse_update_kernel<V, C>,
+    HB_CUDA_OK(cudaFuncSetAttribute(sparse_update_kernel<V, C, OPT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
+  if (P.total_ctas > 0) {
     KernelScope ks(HB_K_SPARSE_UPDATE, stream);
-    sparse_update_kernel<V, C><<<P.total_ctas, kUpdThreads, smem, stream>>>(P);
+    sparse_update_kernel<V, C, OPT><<<P.total_ctas, kUpdThreads, smem, stream>>>(P);
+  }
+  HB_CUDA_OK(cudaGetLastError());
+  if (X.total_ctas > 0) {
+    KernelScope ks(HB_K_SPARSE_FIXUP, stream);
+    sparse_update_fixup_kernel<V, OPT><<<X.total_ctas, kUpdThreads, 0, stream>>>(X);
   }
   HB_CUDA_OK(cudaGetLastError());
   return HB_OK;
+}
+
+template <int V, int C>
+static int launch_update(const UpdParams& P, const UpdParams& X, cudaStream_t stream) {
+  switch (P.opt) {
+    case HB_OPT_ADAGRAD: return launch_update_opt<V, C, HB_OPT_ADAGRAD>(P, X, stream);
+    case HB_OPT_LAZY_ADAM: return launch_update_opt<V, C, HB_OPT_LAZY_ADAM>(P, X, stream);
+    default: return launch_update_opt<V, C, HB_OPT_SGD>(P, X, stream);
+  }
 }
 
 static int validate_upd(int k, const hbUpdateFeature& f, const hbOptimizer* opt) {
@@ -479,7 +561,7 @@ static int validate_upd(int k, const hbUpdateFeature& f, const hbOptimizer* opt)
 // is shared by the features of one call (1 locally, W on a row-interleaved shard).
 int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* opt, void* ws,
                       size_t ws_bytes, int32_t* d_status, cudaStream_t stream,
-                      const WaitSpec* wait) {
+                      const WaitSpec* wait, const int32_t* const* n_dev) {
   HB_REQUIRE(n >= 1 && feats && opt, "update: bad arguments");
   HB_REQUIRE(opt->kind >= HB_OPT_SGD && opt->kind <= HB_OPT_LAZY_ADAM, "update: bad optimizer kind %d", opt->kind);
   for (int k = 0; k < n; ++k) {
@@ -539,50 +621,66 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
       }
     }
 
-    // 2. radix passes; feature k takes part in pass p iff p < passes[k]
-    for (int p = 0; p < max_passes; ++p) {
-      BucketParams bp;
-      bp.nsegs = 0;
-      int tiles = 0;
-      for (int k = 0; k < nc; ++k) {
-        const hbUpdateFeature& f = feats[c0 + k];
-        if (f.nnz == 0 || p >= L[k].passes) continue;
-        BucketSeg& s = bp.seg[bp.nsegs++];
-        uint32_t* kA = reinterpret_cast<uint32_t*>(base + L[k].keysA);
-        uint32_t* kB = reinterpret_cast<uint32_t*>(base + L[k].keysB);
-        int32_t* vA = reinterpret_cast<int32_t*>(base + L[k].valsA);
-        int32_t* vB = reinterpret_cast<int32_t*>(base + L[k].valsB);
-        if (p == 0) {
-          s.in_keys = f.ids;
-          s.in_vals = f.offsets ? reinterpret_cast<int32_t*>(base + L[k].bagmap) : nullptr;
-          s.out_keys = kA;
-          s.out_vals = vA;
-        } else {
-          const bool a2b = (p & 1) == 1;  // pass 1: A->B, pass 2: B->A, ...
-          s.in_keys = a2b ? kA : kB;
-          s.in_vals = a2b ? vA : vB;
-          s.out_keys = a2b ? kB : kA;
-          s.out_vals = a2b ? vB : vA;
+    // 2. LSD radix sort: one memset, one histogram kernel over the ids (all digit
+    //    positions), then one kernel per digit position; feature k takes part in
+    //    pass p iff p < passes[k]
+    if (max_passes > 0) {
+      const size_t words = bucket_scratch_words(nc, (size_t)total_tiles, kRadixBins, max_passes);
+      HB_CUDA_OK(cudaMemsetAsync(counts, 0, words * sizeof(uint32_t), stream));
+      BucketScratch sc = bucket_scratch_carve(reinterpret_cast<uint32_t*>(counts), nc,
+                                              (size_t)total_tiles, kRadixBins, max_passes);
+      for (int p = -1; p < max_passes; ++p) {  // p == -1: histogram launch
+        BucketParams bp;
+        bp.nsegs = 0;
+        int tiles = 0;
+        for (int k = 0; k < nc; ++k) {
+          const hbUpdateFeature& f = feats[c0 + k];
+          if (f.nnz == 0 || (p >= 0 && p >= L[k].passes)) continue;
+          BucketSeg& s = bp.seg[bp.nsegs++];
+          uint32_t* kA = reinterpret_cast<uint32_t*>(base + L[k].keysA);
+          uint32_t* kB = reinterpret_cast<uint32_t*>(base + L[k].keysB);
+          int32_t* vA = reinterpret_cast<int32_t*>(base + L[k].valsA);
+          int32_t* vB = reinterpret_cast<int32_t*>(base + L[k].valsB);
+          if (p <= 0) {
+            s.in_keys = f.ids;
+            s.in_vals = f.offsets ? reinterpret_cast<int32_t*>(base + L[k].bagmap) : nullptr;
+            s.out_keys = kA;
+            s.out_vals = vA;
+          } else {
+            const bool a2b = (p & 1) == 1;  // pass 1: A->B, pass 2: B->A, ...
+            s.in_keys = a2b ? kA : kB;
+            s.in_vals = a2b ? vA : vB;
+            s.out_keys = a2b ? kB : kA;
+            s.out_vals = a2b ? vB : vA;
+          }
+          s.out_inv = nullptr;
+          s.out_sizes = nullptr;
+          s.n = (int32_t)f.nnz;
+          s.n_dev = n_dev ? n_dev[c0 + k] : nullptr;
+          s.tile_begin = tiles;
+          s.shift = (p < 0 ? 0 : p) * kRadixBits;
+          s.key_limit = (uint32_t)f.rows;
+          s.hist_slot = k;
+          s.passes = L[k].passes;
+          tiles += bucket_tiles(f.nnz);
         }
-        s.out_inv = nullptr;
-        s.out_sizes = nullptr;
-        s.n = (int32_t)f.nnz;
-        s.tile_begin = tiles;
-        s.shift = p * kRadixBits;
-        s.key_limit = (uint32_t)f.rows;
-        tiles += bucket_tiles(f.nnz);
+        if (bp.nsegs == 0) break;
+        bp.hist = sc.hist;
+        bp.status = sc.status[p < 0 ? 0 : p];
+        bp.ticket = sc.ticket[p < 0 ? 0 : p];
+        bp.nbins = kRadixBins;
+        bp.total_tiles = tiles;
+        bp.npass = max_passes;
+        bp.pass = p < 0 ? 0 : p;
+        bp.digit_bits = kRadixBits;
+        bp.p = 1; bp.m = 1; bp.pow2_mask = 0;
+        bp.div = feats[0].id_div;
+        bp.div_shift = ((bp.div & (bp.div - 1)) == 0 && bp.div <= (1 << 30)) ? ilog2c(bp.div) : -1;
+        if (p < 0) rc = bucket_hist_launch<RadixFirstTraits>(bp, stream, HB_K_SORT_HIST);
+        else if (p == 0) rc = bucket_pass_launch<RadixFirstTraits>(bp, stream, HB_K_SORT_PASS);
+        else rc = bucket_pass_launch<RadixNextTraits>(bp, stream, HB_K_SORT_PASS);
+        if (rc != HB_OK) return rc;
       }
-      if (bp.nsegs == 0) break;
-      bp.counts = counts;
-      bp.nbins = kRadixBins;
-      bp.total_tiles = tiles;
-      bp.p = 1; bp.m = 1; bp.pow2_mask = 0;
-      bp.div = feats[0].id_div;
-      bp.div_shift = ((bp.div & (bp.div - 1)) == 0 && bp.div <= (1 << 30)) ? ilog2c(bp.div) : -1;
-      bp.pad = 0;
-      rc = (p == 0) ? bucket_pass_launch<RadixFirstTraits>(bp, stream, HB_K_SORT_COUNT)
-                    : bucket_pass_launch<RadixNextTraits>(bp, stream, HB_K_SORT_COUNT);
-      if (rc != HB_OK) return rc;
     }
 
     // 3./4. fused update + fix-up, one launch per V
@@ -615,6 +713,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         F.st_part = reinterpret_cast<float*>(base + L[k].st_part);
         F.st_key = reinterpret_cast<uint32_t*>(base + L[k].st_key);
         F.st_flag = reinterpret_cast<int32_t*>(base + L[k].st_flag);
+        F.n_dev = n_dev ? n_dev[c0 + k] : nullptr;
         F.rows = f.rows; F.grad_stride = f.grad_stride;
         F.n = (int32_t)f.nnz; F.dim = f.dim; F.combiner = f.combiner;
         F.log2g = L[k].log2g;
@@ -627,27 +726,17 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         U.nfeats++;
       }
       if (U.nfeats == 0) continue;
-      switch (V) {
-        case 1: rc = launch_update<1, 8>(U, 0, stream); break;
-        case 2: rc = launch_update<2, 4>(U, 0, stream); break;
-        case 4: rc = launch_update<4, 2>(U, 0, stream); break;
-        default: rc = launch_update<8, 2>(U, 0, stream); break;
-      }
-      if (rc != HB_OK) return rc;
       // fix-up launch: same params, cta_begin re-based to fix-up CTAs
       UpdParams X = U;
       for (int k = 0; k < X.nfeats; ++k) X.f[k].cta_begin = fix_begin[k];
       X.total_ctas = fix_ctas;
-      if (fix_ctas > 0) {
-        KernelScope ks(HB_K_SPARSE_FIXUP, stream);
-        switch (V) {
-          case 1: sparse_update_fixup_kernel<1><<<fix_ctas, kUpdThreads, 0, stream>>>(X); break;
-          case 2: sparse_update_fixup_kernel<2><<<fix_ctas, kUpdThreads, 0, stream>>>(X); break;
-          case 4: sparse_update_fixup_kernel<4><<<fix_ctas, kUpdThreads, 0, stream>>>(X); break;
-          default: sparse_update_fixup_kernel<8><<<fix_ctas, kUpdThreads, 0, stream>>>(X); break;
-        }
-        HB_CUDA_OK(cudaGetLastError());
+      switch (V) {
+        case 1: rc = launch_update<1, 8>(U, X, stream); break;
+        case 2: rc = launch_update<2, 4>(U, X, stream); break;
+        case 4: rc = launch_update<4, 2>(U, X, stream); break;
+        default: rc = launch_update<8, 2>(U, X, stream); break;
       }
+      if (rc != HB_OK) return rc;
     }
   }
   return HB_OK;
@@ -672,7 +761,7 @@ int hbGroupSparseUpdateWorkspaceBytes(int n, const hbUpdateFeature* feats, size_
       o = upd_layout(f, o).end;
       tiles += bucket_tiles(f.nnz);
     }
-    const size_t cb = align_up(tiles * kRadixBins * sizeof(int32_t), 256);
+    const size_t cb = align_up(bucket_scratch_words(nc, tiles, kRadixBins, kMaxPasses) * sizeof(uint32_t), 256);
     if (cb > max_chunk_counts) max_chunk_counts = cb;
   }
   *bytes = o + max_chunk_counts + 256;
@@ -683,7 +772,7 @@ int hbGroupLookupBackwardUpdate(int n, const hbUpdateFeature* feats, const hbOpt
                                 void* d_workspace, size_t workspace_bytes, int32_t* d_status,
                                 hbStream stream) {
   return hb::sparse_update_run(n, feats, opt, d_workspace, workspace_bytes, d_status,
-                               (cudaStream_t)stream, nullptr);
+                               (cudaStream_t)stream, nullptr, nullptr);
 }
 
 }  // extern "C"

@@ -44,8 +44,8 @@ enum { HB_STATUS_ID_OUT_OF_RANGE = 1, HB_STATUS_WINDOW_OVERFLOW = 2,
        HB_STATUS_BAD_OFFSETS = 4 };
 
 /* kernel ids for the launch counter / event profiler */
-enum { HB_K_PART_COUNT = 1, HB_K_PART_SCAN = 2, HB_K_PART_SCATTER = 3,
-       HB_K_SORT_COUNT = 4, HB_K_SORT_SCAN = 5, HB_K_SORT_SCATTER = 6,
+enum { HB_K_PART_HIST = 1, HB_K_PART_PASS = 2, HB_K_RESERVED3 = 3,
+       HB_K_SORT_HIST = 4, HB_K_SORT_PASS = 5, HB_K_RESERVED6 = 6,
        HB_K_BAG_MAP = 7, HB_K_LOOKUP_FWD = 8, HB_K_SPARSE_UPDATE = 9,
        HB_K_SPARSE_FIXUP = 10, HB_K_CAST = 11, HB_K_CACHE_LOOKUP = 12,
        HB_K_BARRIER = 13, HB_K_A2A_SIZES = 14, HB_K_A2A_TABLES = 15,
