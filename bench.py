@@ -154,23 +154,50 @@ def cpu_arm(args, sizes, dim, steps, warmup, rank0_only_note=''):
       if accs is not None:
         accs[k][u] = 0.1
 
-  def one_feature(k, ids):
-    o.embedding_lookup_sparse(tables[k], ids, offsets, 'mean', out=out[:, k * dim:(k + 1) * dim])
-    if accs is not None:
-      rg = o.lookup_row_grads(grad[:, k * dim:(k + 1) * dim], offsets, 'mean')
-      o.sparse_apply_adagrad(tables[k], accs[k], ids, rg, 0.01)
+  # Work decomposition that uses every host core: the forward splits each feature
+  # into bag chunks (independent); the backward of a big table is split by
+  # id % parts (disjoint row sets, so the per-part dedup + Adagrad apply are
+  # independent and together equal the unsplit update).
+  fwd_chunks = max(1, min(8, cores // F))
+  bounds = np.linspace(0, B, fwd_chunks + 1).astype(np.int64)
 
-  workers = min(cores, F)
+  def fwd_task(k, c, ids):
+    s, e = int(bounds[c]), int(bounds[c + 1])
+    o.embedding_lookup_sparse(tables[k], ids[s:e], offsets[:e - s + 1], 'mean',
+                              out=out[s:e, k * dim:(k + 1) * dim])
+
+  def parts_of(k):
+    return max(1, min(8, cores // F)) if csizes[k] > 1000000 else 1
+
+  def bwd_task(k, part, parts, ids):
+    if parts == 1:
+      sel_ids, g = ids, grad[:, k * dim:(k + 1) * dim]
+    else:
+      sel = np.nonzero(ids % parts == part)[0]
+      sel_ids, g = ids[sel], grad[sel, k * dim:(k + 1) * dim]
+    # mean combiner with one id per bag: row gradient == bag gradient
+    o.sparse_apply_adagrad(tables[k], accs[k], sel_ids, np.ascontiguousarray(g), 0.01)
+
+  workers = cores
+  ntasks = F * fwd_chunks
   with ThreadPoolExecutor(workers) as ex:
     def step(i):
       b = batches[i % nb]
-      list(ex.map(lambda k: one_feature(k, b[k]), range(F)))
+      futs = [ex.submit(fwd_task, k, c, b[k]) for k in range(F) for c in range(fwd_chunks)]
+      for f in futs:
+        f.result()
+      if accs is not None:
+        futs = [ex.submit(bwd_task, k, p, parts_of(k), b[k]) for k in range(F)
+                for p in range(parts_of(k))]
+        for f in futs:
+          f.result()
     for i in range(warmup):
       step(i)
     t0 = time.perf_counter()
     for i in range(steps):
       step(i)
     dt = time.perf_counter() - t0
+  workers = min(cores, ntasks)
   value = B * F * steps / dt
   info = {'value': value, 'unit': 'pooled-embedding-rows/s', 'cores': workers,
           'host_cores': cores,
@@ -178,7 +205,7 @@ def cpu_arm(args, sizes, dim, steps, warmup, rank0_only_note=''):
           'sample': (f'{steps} steps x (26 feats x {B} ids) of the same workload, '
                      f'{"fwd+bwd+Adagrad" if args.mode == "train" else "fwd"}, tables '
                      f'{"full size" if scale == 1.0 else f"scaled x{scale:.2f} to fit host RAM"}, '
-                     f'{workers} threads (one per feature); oracle/hb_oracle.c port of the '
+                     f'{workers} threads (forward: feature x bag-chunk tasks, backward: feature x id%parts tasks); oracle/hb_oracle.c port of the '
                      'TF-1.15 CPU semantics (the tf115 wheel cannot run here)' + rank0_only_note),
           'ms_per_step': dt / steps * 1e3}
   return value, info

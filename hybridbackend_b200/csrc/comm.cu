@@ -214,10 +214,10 @@ a2a_push_kernel(const __grid_constant__ PushParams P, PeerPtrs peers, int me, in
     }
   }
   // publish: the last CTA to finish releases the epoch flag on every peer
-  __threadfence_system();
   __syncthreads();
   __shared__ bool s_last;
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned done = atomicAdd(&mine->done_counter[half], 1u);
     s_last = (done == gridDim.x - 1);
     if (s_last) mine->done_counter[half] = 0;

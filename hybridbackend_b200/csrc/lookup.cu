@@ -81,109 +81,141 @@ __device__ __forceinline__ int64_t row_of(const LookupFeat& F, int64_t p) {
   return local_row(ld_nc_i64(F.ids + p), F);
 }
 
+// Row indices of the kBagsPerGroup bags a group owns in chunk `cid` of a
+// one-id-per-bag feature: >= 0 row, -1 out-of-range id, -2 no such bag.
+__device__ __forceinline__ void load_rows(const LookupFeat& F, int cid, int64_t (&r)[kBagsPerGroup],
+                                          bool& oob) {
+  const int groups = kLookupThreads >> F.log2g;
+  const int g = threadIdx.x >> F.log2g;
+  const int bag0 = (cid - F.cta_begin) * groups * kBagsPerGroup;
+#pragma unroll
+  for (int u = 0; u < kBagsPerGroup; ++u) {
+    const int b = bag0 + u * groups + g;
+    r[u] = -2;
+    if (b < F.nbags) {
+      r[u] = row_of(F, b);
+      if ((uint64_t)r[u] >= (uint64_t)F.rows) { oob = true; r[u] = -1; }
+    }
+  }
+}
+
+// Persistent CTAs walk the chunk list (chunk = groups*kBagsPerGroup bags of one
+// feature).  For one-id-per-bag features the row indices of the NEXT chunk are
+// fetched while the rows of the current chunk are in flight, so every iteration
+// exposes a single memory round trip with 4 x 128-bit loads per lane outstanding.
 template <int V, bool COH>
 __global__ void __launch_bounds__(kLookupThreads)
 lookup_fwd_kernel(const __grid_constant__ LookupParams P) {
   wait_spec(P.wait);
-  const int fi = find_feat(P, blockIdx.x);
-  const LookupFeat& F = P.f[fi];
-  const int chunk = blockIdx.x - F.cta_begin;
-  const int log2g = F.log2g;
-  const int groups = kLookupThreads >> log2g;
-  const int g = threadIdx.x >> log2g;
-  const int l = threadIdx.x & ((1 << log2g) - 1);
-  const int dim = F.dim;
-  const int nbags = F.nbags;
-  const int bag0 = chunk * groups * kBagsPerGroup;
   bool oob = false;
   bool bad_off = false;
+  int cid = blockIdx.x;
+  if (cid >= P.total_ctas) return;
+  int fi = find_feat(P, cid);
+  int64_t r[kBagsPerGroup];
+#pragma unroll
+  for (int u = 0; u < kBagsPerGroup; ++u) r[u] = -2;
+  if (P.f[fi].offsets == nullptr) load_rows(P.f[fi], cid, r, oob);
 
-  // column c of lane l, vector v:  (v * G + l) * 4
-  int col[V];
-  bool act[V];
+  while (true) {
+    const LookupFeat& F = P.f[fi];
+    const int log2g = F.log2g;
+    const int groups = kLookupThreads >> log2g;
+    const int g = threadIdx.x >> log2g;
+    const int l = threadIdx.x & ((1 << log2g) - 1);
+    const int dim = F.dim;
+    const int nbags = F.nbags;
+    const int bag0 = (cid - F.cta_begin) * groups * kBagsPerGroup;
+    // column c of lane l, vector v:  (v * G + l) * 4
+    int col[V];
+    bool act[V];
 #pragma unroll
-  for (int v = 0; v < V; ++v) {
-    col[v] = ((v << log2g) + l) * 4;
-    act[v] = col[v] < dim;
-  }
+    for (int v = 0; v < V; ++v) {
+      col[v] = ((v << log2g) + l) * 4;
+      act[v] = col[v] < dim;
+    }
+    const int nid = cid + gridDim.x;
+    const int nfi = (nid < P.total_ctas) ? find_feat(P, nid) : -1;
+    int64_t rn[kBagsPerGroup];
+#pragma unroll
+    for (int u = 0; u < kBagsPerGroup; ++u) rn[u] = -2;
 
-  if (F.offsets == nullptr) {
-    // ---- one id per bag: pure gather, kBagsPerGroup rows in flight ----------
-    int64_t r[kBagsPerGroup];
-    bool ok[kBagsPerGroup];
+    if (F.offsets == nullptr) {
+      // ---- one id per bag: pure gather ---------------------------------------
+      float4 val[kBagsPerGroup][V];
 #pragma unroll
-    for (int u = 0; u < kBagsPerGroup; ++u) {
-      const int b = bag0 + u * groups + g;
-      ok[u] = b < nbags;
-      r[u] = ok[u] ? row_of(F, b) : 0;
-      if (ok[u] && (uint64_t)r[u] >= (uint64_t)F.rows) { oob = true; r[u] = -1; }
-    }
-    float4 val[kBagsPerGroup][V];
+      for (int u = 0; u < kBagsPerGroup; ++u)
 #pragma unroll
-    for (int u = 0; u < kBagsPerGroup; ++u)
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok[u] && r[u] >= 0 && act[v])
-          val[u][v] = ld_row4<COH>(reinterpret_cast<const float4*>(F.table + r[u] * dim + col[v]));
-      }
-#pragma unroll
-    for (int u = 0; u < kBagsPerGroup; ++u) {
-      const int b = bag0 + u * groups + g;
-      if (!ok[u]) continue;
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (act[v])
-          *reinterpret_cast<float4*>(F.out + (int64_t)b * F.out_stride + col[v]) = val[u][v];
-    }
-  } else {
-    // ---- CSR bags: sequential fp32 accumulation in bag order ----------------
-#pragma unroll 1
-    for (int u = 0; u < kBagsPerGroup; ++u) {
-      const int b = bag0 + u * groups + g;
-      if (b >= nbags) break;
-      int64_t s = F.offsets[b];
-      int64_t e = F.offsets[b + 1];
-      if (e < s || s < 0) { bad_off = true; e = s; }
-      float4 acc[V];
-#pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int64_t p = s; p < e; p += 4) {
-        int64_t r[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          r[k] = -1;
-          if (p + k < e) {
-            r[k] = row_of(F, p + k);
-            if ((uint64_t)r[k] >= (uint64_t)F.rows) { oob = true; r[k] = -1; }
-          }
+        for (int v = 0; v < V; ++v) {
+          val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r[u] >= 0 && act[v])
+            val[u][v] = ld_row4<COH>(reinterpret_cast<const float4*>(F.table + r[u] * dim + col[v]));
         }
-        float4 x[4][V];
+      if (nfi >= 0 && P.f[nfi].offsets == nullptr) load_rows(P.f[nfi], nid, rn, oob);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+      for (int u = 0; u < kBagsPerGroup; ++u) {
+        const int b = bag0 + u * groups + g;
+        if (r[u] == -2) continue;
 #pragma unroll
-          for (int v = 0; v < V; ++v) {
-            x[k][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r[k] >= 0 && act[v])
-              x[k][v] = ld_row4<COH>(reinterpret_cast<const float4*>(F.table + r[k] * dim + col[v]));
+        for (int v = 0; v < V; ++v)
+          if (act[v])
+            *reinterpret_cast<float4*>(F.out + (int64_t)b * F.out_stride + col[v]) = val[u][v];
+      }
+    } else {
+      // ---- CSR bags: sequential fp32 accumulation in bag order ----------------
+#pragma unroll 1
+      for (int u = 0; u < kBagsPerGroup; ++u) {
+        const int b = bag0 + u * groups + g;
+        if (b >= nbags) break;
+        int64_t s = F.offsets[b];
+        int64_t e = F.offsets[b + 1];
+        if (e < s || s < 0) { bad_off = true; e = s; }
+        float4 acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t p = s; p < e; p += 4) {
+          int64_t rr[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            rr[k] = -1;
+            if (p + k < e) {
+              rr[k] = row_of(F, p + k);
+              if ((uint64_t)rr[k] >= (uint64_t)F.rows) { oob = true; rr[k] = -1; }
+            }
           }
+          float4 x[4][V];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (p + k < e)
+          for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int v = 0; v < V; ++v) acc[v] = f4_add(acc[v], x[k][v]);
+            for (int v = 0; v < V; ++v) {
+              x[k][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (rr[k] >= 0 && act[v])
+                x[k][v] = ld_row4<COH>(reinterpret_cast<const float4*>(F.table + rr[k] * dim + col[v]));
+            }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (p + k < e)
+#pragma unroll
+              for (int v = 0; v < V; ++v) acc[v] = f4_add(acc[v], x[k][v]);
+        }
+        const int64_t cnt = e - s;
+        if (cnt > 0 && F.combiner != HB_SUM) {
+          const float c = (F.combiner == HB_MEAN) ? (float)cnt : __fsqrt_rn((float)cnt);
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = f4_div(acc[v], c);
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (act[v])
+            *reinterpret_cast<float4*>(F.out + (int64_t)b * F.out_stride + col[v]) = acc[v];
       }
-      const int64_t cnt = e - s;
-      if (cnt > 0 && F.combiner != HB_SUM) {
-        const float c = (F.combiner == HB_MEAN) ? (float)cnt : __fsqrt_rn((float)cnt);
-#pragma unroll
-        for (int v = 0; v < V; ++v) acc[v] = f4_div(acc[v], c);
-      }
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (act[v])
-          *reinterpret_cast<float4*>(F.out + (int64_t)b * F.out_stride + col[v]) = acc[v];
+      if (nfi >= 0 && P.f[nfi].offsets == nullptr) load_rows(P.f[nfi], nid, rn, oob);
     }
+    if (nfi < 0) break;
+    cid = nid;
+    fi = nfi;
+#pragma unroll
+    for (int u = 0; u < kBagsPerGroup; ++u) r[u] = rn[u];
   }
   if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
   if (bad_off) raise_status(P.status, HB_STATUS_BAD_OFFSETS);
@@ -210,9 +242,17 @@ template <int V>
 static int launch_lookup(const LookupParams& P, cudaStream_t stream, bool coherent, int kid) {
   if (P.total_ctas == 0) return HB_OK;
   {
+    // persistent: exactly the co-resident number of CTAs walks all chunks
+    int per_sm = 0;
+    if (coherent)
+      HB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lookup_fwd_kernel<V, true>, kLookupThreads, 0));
+    else
+      HB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lookup_fwd_kernel<V, false>, kLookupThreads, 0));
+    const int maxg = device_sm_count() * (per_sm > 0 ? per_sm : 1);
+    const int grid = P.total_ctas < maxg ? P.total_ctas : maxg;
     KernelScope ks(kid, stream);
-    if (coherent) lookup_fwd_kernel<V, true><<<P.total_ctas, kLookupThreads, 0, stream>>>(P);
-    else lookup_fwd_kernel<V, false><<<P.total_ctas, kLookupThreads, 0, stream>>>(P);
+    if (coherent) lookup_fwd_kernel<V, true><<<grid, kLookupThreads, 0, stream>>>(P);
+    else lookup_fwd_kernel<V, false><<<grid, kLookupThreads, 0, stream>>>(P);
   }
   HB_CUDA_OK(cudaGetLastError());
   return HB_OK;

@@ -89,11 +89,14 @@ __device__ __forceinline__ unsigned char* win(const ShParams& P, int r) {
 
 // last-CTA-done: publish `epoch` into flag slot `phase` of every peer
 __device__ __forceinline__ void signal_all_peers(const ShParams& P, int phase, int counter) {
-  __threadfence_system();
+  // CTA barrier, then ONE system fence by thread 0: the barrier orders every
+  // thread's peer stores before the fence, the fence makes them visible system
+  // wide before the counter/flag updates (cooperative-groups grid.sync pattern)
   __syncthreads();
   __shared__ bool s_last;
   Control* mine = ctl(P, P.me);
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned done = atomicAdd(&mine->done_counter[counter], 1u);
     s_last = (done == gridDim.x - 1);
     if (s_last) mine->done_counter[counter] = 0;
@@ -209,67 +212,70 @@ constexpr int kShRowsPerGroup = 4;
 template <int V>
 __global__ void __launch_bounds__(256) sh_owner_gather_kernel(const __grid_constant__ ShParams P) {
   wait_all_peers(P, 1);
-  int lo = 0, hi = P.n - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (P.f[mid].cta_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-  }
-  const ShFeat& F = P.f[lo];
-  const ShFeatMeta& m = P.meta[lo];
-  const int log2g = F.log2g;
-  const int groups = 256 >> log2g;
-  const int g = threadIdx.x >> log2g;
-  const int l = threadIdx.x & ((1 << log2g) - 1);
-  const int dim = F.dim;
-  const int chunk = blockIdx.x - F.cta_begin;
-  const int p0 = chunk * groups * kShRowsPerGroup;
-  const int total = m.recv_clamped;
-  int64_t* ids_in = reinterpret_cast<int64_t*>(win(P, P.me) + F.ids_in_off[P.parity]);
   bool oob = false;
-  int col[V];
-  bool act[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    col[v] = ((v << log2g) + l) * 4;
-    act[v] = col[v] < dim;
-  }
-  int64_t row[kShRowsPerGroup];
-  int q[kShRowsPerGroup];
-  int dstrow[kShRowsPerGroup];
-  bool ok[kShRowsPerGroup];
-#pragma unroll
-  for (int u = 0; u < kShRowsPerGroup; ++u) {
-    const int p = p0 + u * groups + g;
-    ok[u] = p < total;
-    row[u] = -1; q[u] = 0; dstrow[u] = 0;
-    if (ok[u]) {
-      const int64_t id = ids_in[p];
-      int64_t r = -1;
-      if (id >= 0) r = P.div_shift >= 0 ? (int64_t)((uint64_t)id >> P.div_shift) : id / P.world;
-      if ((uint64_t)r >= (uint64_t)F.shard_rows) { oob = true; r = -1; }
-      row[u] = r;
-      int qq = 0;
-      while (qq + 1 < P.world && m.recv_base[qq + 1] <= p) ++qq;
-      q[u] = qq;
-      dstrow[u] = m.src_bucket_off[qq] + (p - m.recv_base[qq]);
+  // persistent CTAs: chunk -> (feature, first received position)
+  for (int chunk_id = blockIdx.x; chunk_id < P.total_ctas; chunk_id += gridDim.x) {
+    int lo = 0, hi = P.n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (P.f[mid].cta_begin <= chunk_id) lo = mid; else hi = mid - 1;
     }
-  }
-  float4 val[kShRowsPerGroup][V];
-#pragma unroll
-  for (int u = 0; u < kShRowsPerGroup; ++u)
+    const ShFeat& F = P.f[lo];
+    const ShFeatMeta& m = P.meta[lo];
+    const int log2g = F.log2g;
+    const int groups = 256 >> log2g;
+    const int g = threadIdx.x >> log2g;
+    const int l = threadIdx.x & ((1 << log2g) - 1);
+    const int dim = F.dim;
+    const int p0 = (chunk_id - F.cta_begin) * groups * kShRowsPerGroup;
+    const int total = m.recv_clamped;
+    if (p0 >= total) continue;
+    const int64_t* ids_in = reinterpret_cast<const int64_t*>(win(P, P.me) + F.ids_in_off[P.parity]);
+    int col[V];
+    bool act[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok[u] && row[u] >= 0 && act[v])
-        val[u][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.shard + row[u] * dim + col[v]));
+      col[v] = ((v << log2g) + l) * 4;
+      act[v] = col[v] < dim;
     }
+    int64_t row[kShRowsPerGroup];
+    int q[kShRowsPerGroup];
+    int dstrow[kShRowsPerGroup];
+    bool ok[kShRowsPerGroup];
 #pragma unroll
-  for (int u = 0; u < kShRowsPerGroup; ++u) {
-    if (!ok[u]) continue;
-    float* dst = reinterpret_cast<float*>(win(P, q[u]) + F.rows_in_off) + (int64_t)dstrow[u] * dim;
+    for (int u = 0; u < kShRowsPerGroup; ++u) {
+      const int p = p0 + u * groups + g;
+      ok[u] = p < total;
+      row[u] = -1; q[u] = 0; dstrow[u] = 0;
+      if (ok[u]) {
+        const int64_t id = ids_in[p];
+        int64_t r = -1;
+        if (id >= 0) r = P.div_shift >= 0 ? (int64_t)((uint64_t)id >> P.div_shift) : id / P.world;
+        if ((uint64_t)r >= (uint64_t)F.shard_rows) { oob = true; r = -1; }
+        row[u] = r;
+        int qq = 0;
+        while (qq + 1 < P.world && m.recv_base[qq + 1] <= p) ++qq;
+        q[u] = qq;
+        dstrow[u] = m.src_bucket_off[qq] + (p - m.recv_base[qq]);
+      }
+    }
+    float4 val[kShRowsPerGroup][V];
 #pragma unroll
-    for (int v = 0; v < V; ++v)
-      if (act[v]) *reinterpret_cast<float4*>(dst + col[v]) = val[u][v];
+    for (int u = 0; u < kShRowsPerGroup; ++u)
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[u] && row[u] >= 0 && act[v])
+          val[u][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.shard + row[u] * dim + col[v]));
+      }
+#pragma unroll
+    for (int u = 0; u < kShRowsPerGroup; ++u) {
+      if (!ok[u]) continue;
+      float* dst = reinterpret_cast<float*>(win(P, q[u]) + F.rows_in_off) + (int64_t)dstrow[u] * dim;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (act[v]) *reinterpret_cast<float4*>(dst + col[v]) = val[u][v];
+    }
   }
   if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
   signal_all_peers(P, 2, 3);
@@ -278,71 +284,74 @@ __global__ void __launch_bounds__(256) sh_owner_gather_kernel(const __grid_const
 // ---- backward: push row gradients to the owners ----------------------------------------
 template <int V>
 __global__ void __launch_bounds__(256) sh_push_grads_kernel(const __grid_constant__ ShParams P) {
-  int lo = 0, hi = P.n - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (P.f[mid].cta_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-  }
-  const ShFeat& F = P.f[lo];
-  const ShFeatMeta& m = P.meta[lo];
-  const int log2g = F.log2g;
-  const int groups = 256 >> log2g;
-  const int g = threadIdx.x >> log2g;
-  const int l = threadIdx.x & ((1 << log2g) - 1);
-  const int dim = F.dim;
-  const int chunk = blockIdx.x - F.cta_begin;
-  const int p0 = chunk * groups * kShRowsPerGroup;
-  int col[V];
-  bool act[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    col[v] = ((v << log2g) + l) * 4;
-    act[v] = col[v] < dim;
-  }
-  int bag[kShRowsPerGroup], r[kShRowsPerGroup], drow[kShRowsPerGroup];
-  float sc[kShRowsPerGroup];
-  bool ok[kShRowsPerGroup];
-#pragma unroll
-  for (int u = 0; u < kShRowsPerGroup; ++u) {
-    const int p = p0 + u * groups + g;
-    ok[u] = p < F.nnz;
-    bag[u] = 0; r[u] = 0; drow[u] = 0; sc[u] = 1.0f;
-    if (ok[u]) {
-      bag[u] = F.bag_of_pos != nullptr && F.offsets != nullptr ? F.bag_of_pos[p] : p;
-      if (F.offsets != nullptr && F.combiner != HB_SUM) {
-        const int64_t c = F.offsets[bag[u] + 1] - F.offsets[bag[u]];
-        sc[u] = (F.combiner == HB_MEAN) ? (float)c : __fsqrt_rn((float)c);
-      }
-      const int j = F.part_idx[p];
-      int rr = 0;
-      while (rr + 1 < P.world && m.send_off[rr + 1] <= j) ++rr;
-      r[u] = rr;
-      drow[u] = m.remote_base[rr] + (j - m.send_off[rr]);
-      if (drow[u] >= F.cap) ok[u] = false;  // overflow already flagged by the exchange
+  for (int chunk_id = blockIdx.x; chunk_id < P.total_ctas; chunk_id += gridDim.x) {
+    int lo = 0, hi = P.n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (P.f[mid].cta_begin <= chunk_id) lo = mid; else hi = mid - 1;
     }
-  }
-  float4 val[kShRowsPerGroup][V];
-#pragma unroll
-  for (int u = 0; u < kShRowsPerGroup; ++u)
+    const ShFeat& F = P.f[lo];
+    const ShFeatMeta& m = P.meta[lo];
+    const int log2g = F.log2g;
+    const int groups = 256 >> log2g;
+    const int g = threadIdx.x >> log2g;
+    const int l = threadIdx.x & ((1 << log2g) - 1);
+    const int dim = F.dim;
+    const int p0 = (chunk_id - F.cta_begin) * groups * kShRowsPerGroup;
+    if (p0 >= F.nnz) continue;
+    const bool scaled = F.offsets != nullptr && F.combiner != HB_SUM;
+    int col[V];
+    bool act[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok[u] && act[v])
-        val[u][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.grad + (int64_t)bag[u] * F.grad_stride + col[v]));
+      col[v] = ((v << log2g) + l) * 4;
+      act[v] = col[v] < dim;
     }
+    int bag[kShRowsPerGroup], r[kShRowsPerGroup], drow[kShRowsPerGroup];
+    float sc[kShRowsPerGroup];
+    bool ok[kShRowsPerGroup];
 #pragma unroll
-  for (int u = 0; u < kShRowsPerGroup; ++u) {
-    if (!ok[u]) continue;
-    float* dst = reinterpret_cast<float*>(win(P, r[u]) + F.grads_in_off) + (int64_t)drow[u] * dim;
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-      if (act[v]) {
-        float4 x = val[u][v];
-        if (F.offsets != nullptr && F.combiner != HB_SUM)
-          x = make_float4(__fdiv_rn(x.x, sc[u]), __fdiv_rn(x.y, sc[u]), __fdiv_rn(x.z, sc[u]),
-                          __fdiv_rn(x.w, sc[u]));
-        *reinterpret_cast<float4*>(dst + col[v]) = x;
+    for (int u = 0; u < kShRowsPerGroup; ++u) {
+      const int p = p0 + u * groups + g;
+      ok[u] = p < F.nnz;
+      bag[u] = 0; r[u] = 0; drow[u] = 0; sc[u] = 1.0f;
+      if (ok[u]) {
+        bag[u] = F.offsets != nullptr ? F.bag_of_pos[p] : p;
+        if (scaled) {
+          const int64_t c = F.offsets[bag[u] + 1] - F.offsets[bag[u]];
+          sc[u] = (F.combiner == HB_MEAN) ? (float)c : __fsqrt_rn((float)c);
+        }
+        const int j = F.part_idx[p];
+        int rr = 0;
+        while (rr + 1 < P.world && m.send_off[rr + 1] <= j) ++rr;
+        r[u] = rr;
+        drow[u] = m.remote_base[rr] + (j - m.send_off[rr]);
+        if (drow[u] >= F.cap) ok[u] = false;  // overflow already flagged by the exchange
       }
+    }
+    float4 val[kShRowsPerGroup][V];
+#pragma unroll
+    for (int u = 0; u < kShRowsPerGroup; ++u)
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[u] && act[v])
+          val[u][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.grad + (int64_t)bag[u] * F.grad_stride + col[v]));
+      }
+#pragma unroll
+    for (int u = 0; u < kShRowsPerGroup; ++u) {
+      if (!ok[u]) continue;
+      float* dst = reinterpret_cast<float*>(win(P, r[u]) + F.grads_in_off) + (int64_t)drow[u] * dim;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (act[v]) {
+          float4 x = val[u][v];
+          if (scaled)
+            x = make_float4(__fdiv_rn(x.x, sc[u]), __fdiv_rn(x.y, sc[u]), __fdiv_rn(x.z, sc[u]),
+                            __fdiv_rn(x.w, sc[u]));
+          *reinterpret_cast<float4*>(dst + col[v]) = x;
+        }
+    }
   }
   signal_all_peers(P, 3, 4);
 }
@@ -672,12 +681,14 @@ int hbShardedLookupForward(hbShardedPlan* pl, const hbShardedFeature* feats, int
     HB_REQUIRE(m == n, "hbShardedLookupForward: all sharded features of a plan must share dim <= 128 or the same V");
     Q.n = m;
     Q.total_ctas = ctas;
+    const int maxg = device_sm_count() * 8;
+    const int grid = ctas < maxg ? ctas : maxg;
     KernelScope ks(HB_K_SH_OWNER_GATHER, stream);
     switch (V) {
-      case 1: sh_owner_gather_kernel<1><<<ctas, 256, 0, stream>>>(Q); break;
-      case 2: sh_owner_gather_kernel<2><<<ctas, 256, 0, stream>>>(Q); break;
-      case 4: sh_owner_gather_kernel<4><<<ctas, 256, 0, stream>>>(Q); break;
-      default: sh_owner_gather_kernel<8><<<ctas, 256, 0, stream>>>(Q); break;
+      case 1: sh_owner_gather_kernel<1><<<grid, 256, 0, stream>>>(Q); break;
+      case 2: sh_owner_gather_kernel<2><<<grid, 256, 0, stream>>>(Q); break;
+      case 4: sh_owner_gather_kernel<4><<<grid, 256, 0, stream>>>(Q); break;
+      default: sh_owner_gather_kernel<8><<<grid, 256, 0, stream>>>(Q); break;
     }
   }
   HB_CUDA_OK(cudaGetLastError());
@@ -752,12 +763,14 @@ int hbShardedLookupBackwardUpdate(hbShardedPlan* pl, const hbShardedFeature* fea
     if (m == 0) continue;
     HB_REQUIRE(m == n, "hbShardedLookupBackwardUpdate: all sharded features of a plan must share V");
     Q.total_ctas = ctas;
+    const int maxg = device_sm_count() * 8;
+    const int grid = ctas < maxg ? ctas : maxg;
     KernelScope ks(HB_K_SH_PUSH_GRADS, stream);
     switch (V) {
-      case 1: sh_push_grads_kernel<1><<<ctas, 256, 0, stream>>>(Q); break;
-      case 2: sh_push_grads_kernel<2><<<ctas, 256, 0, stream>>>(Q); break;
-      case 4: sh_push_grads_kernel<4><<<ctas, 256, 0, stream>>>(Q); break;
-      default: sh_push_grads_kernel<8><<<ctas, 256, 0, stream>>>(Q); break;
+      case 1: sh_push_grads_kernel<1><<<grid, 256, 0, stream>>>(Q); break;
+      case 2: sh_push_grads_kernel<2><<<grid, 256, 0, stream>>>(Q); break;
+      case 4: sh_push_grads_kernel<4><<<grid, 256, 0, stream>>>(Q); break;
+      default: sh_push_grads_kernel<8><<<grid, 256, 0, stream>>>(Q); break;
     }
   }
   HB_CUDA_OK(cudaGetLastError());

@@ -132,7 +132,7 @@ def test_alltoallv_vs_oracle_2gpu():
 def _sharded_lookup(rank, world, hb, o):
   dev = torch.device('cuda', rank)
   rng = np.random.RandomState(11)  # shared
-  sizes = [1003, 40000, 7, 250000]   # 7 rows -> "small" (replicated) table
+  sizes = [1003, 40000, 2, 250000]   # 2 rows <= W -> "small" (replicated) table
   D, B = 32, 3000
   full = [rng.uniform(-0.1, 0.1, (n, D)).astype(np.float32) for n in sizes]
   feats_all = []

@@ -85,7 +85,8 @@ def test_adagrad_hot_rows_tiny_tables(hb, oracle):
 
 
 def test_adagrad_zipf(hb, oracle):
-  _run(hb, oracle, 'adagrad', 'mean', [1543, 39043, 403346], 32, 30000, one_hot=True, zipf=True)
+  # zipf: hot rows sum hundreds of gradients (see the tolerance note above)
+  _run(hb, oracle, 'adagrad', 'mean', [1543, 39043, 403346], 32, 30000, one_hot=True, zipf=True, rtol=2e-4)
 
 
 @pytest.mark.parametrize('dim', [4, 16, 64, 128, 256])
@@ -95,7 +96,7 @@ def test_adagrad_dims(hb, oracle, dim):
 
 def test_lazy_adam(hb, oracle):
   _run(hb, oracle, 'lazy_adam', 'mean', [20000, 300], 16, 5000, steps=3)
-  _run(hb, oracle, 'lazy_adam', 'sum', [100000], 128, 4096, steps=2, one_hot=True, zipf=True)
+  _run(hb, oracle, 'lazy_adam', 'sum', [100000], 128, 4096, steps=2, one_hot=True, zipf=True, rtol=2e-4)
 
 
 def test_determinism(hb):
