@@ -158,6 +158,31 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
   return v;
 }
 
+// Block-wide exclusive scan of one int per thread (256 threads): warp shuffles +
+// one smem hop; returns the exclusive prefix, *total gets the block sum.
+__device__ __forceinline__ int32_t block_excl_scan(int32_t x, int32_t* s_warp /*[8]*/, int32_t* total) {
+  const unsigned lane = threadIdx.x & 31u;
+  const int warp = threadIdx.x >> 5;
+  int32_t incl = x;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int32_t y = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= (unsigned)off) incl += y;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int32_t wbase = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kBucketWarps; ++w) {
+    const int32_t t = s_warp[w];
+    if (w < warp) wbase += t;
+    tot += t;
+  }
+  __syncthreads();
+  if (total != nullptr) *total = tot;
+  return wbase + incl - x;
+}
+
 // ---- hist -------------------------------------------------------------------
 // Histograms of every digit position of every segment in one read of the input.
 template <typename Tr>
@@ -305,15 +330,7 @@ bucket_pass_kernel(const __grid_constant__ BucketParams P) {
       h[k] = (b < nb) ? (int32_t)gh[b] : 0;
       hsum += h[k];
     }
-    s_scan[threadIdx.x] = hsum;
-    __syncthreads();
-    for (int off = 1; off < kBucketThreads; off <<= 1) {
-      int32_t add = (threadIdx.x >= off) ? s_scan[threadIdx.x - off] : 0;
-      __syncthreads();
-      s_scan[threadIdx.x] += add;
-      __syncthreads();
-    }
-    int32_t run = s_scan[threadIdx.x] - hsum;
+    int32_t run = block_excl_scan(hsum, s_scan, nullptr);
 #pragma unroll
     for (int k = 0; k < kBinsPerThread; ++k) {
       const int b = threadIdx.x * kBinsPerThread + k;
@@ -329,31 +346,37 @@ bucket_pass_kernel(const __grid_constant__ BucketParams P) {
     }
   }
   __syncthreads();
-  // ... plus the counts of all preceding tiles of this segment: independent loads,
-  // 8 in flight per thread, spinning only on words not yet published
+  // ... plus the counts of all preceding tiles of this segment: independent loads
+  // (both bins of the thread, 8 tiles each = 16 in flight), spinning only on words
+  // not yet published
+  {
+    const uint32_t* st = P.status + (size_t)sg.tile_begin * nb;
+    int32_t pre[kBinsPerThread];
 #pragma unroll
-  for (int k = 0; k < kBinsPerThread; ++k) {
-    const int b = k * kBucketThreads + threadIdx.x;
-    if (b < nb) {
-      const uint32_t* st = P.status + (size_t)sg.tile_begin * nb + b;
-      int32_t pre = 0;
-      int tp = 0;
-      for (; tp + 8 <= t; tp += 8) {
-        uint32_t v[8];
+    for (int k = 0; k < kBinsPerThread; ++k) pre[k] = 0;
+    for (int tp = 0; tp < t; tp += 8) {
+      uint32_t v[kBinsPerThread][8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = ld_volatile_u32(st + (size_t)(tp + u) * nb);
+      for (int k = 0; k < kBinsPerThread; ++k) {
+        const int b = k * kBucketThreads + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          v[k][u] = (b < nb && tp + u < t) ? ld_volatile_u32(st + (size_t)(tp + u) * nb + b) : kReady;
+      }
+#pragma unroll
+      for (int k = 0; k < kBinsPerThread; ++k) {
+        const int b = k * kBucketThreads + threadIdx.x;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          while (!(v[u] & kReady)) v[u] = ld_volatile_u32(st + (size_t)(tp + u) * nb);
-          pre += (int32_t)(v[u] & ~kReady);
+          while (!(v[k][u] & kReady)) v[k][u] = ld_volatile_u32(st + (size_t)(tp + u) * nb + b);
+          pre[k] += (int32_t)(v[k][u] & ~kReady);
         }
       }
-      for (; tp < t; ++tp) {
-        uint32_t v = ld_volatile_u32(st + (size_t)tp * nb);
-        while (!(v & kReady)) v = ld_volatile_u32(st + (size_t)tp * nb);
-        pre += (int32_t)(v & ~kReady);
-      }
-      s_gbase[b] += pre;
+    }
+#pragma unroll
+    for (int k = 0; k < kBinsPerThread; ++k) {
+      const int b = k * kBucketThreads + threadIdx.x;
+      if (b < nb) s_gbase[b] += pre[k];
     }
   }
   // local bin starts inside the tile (exclusive scan of tile totals, bin order)
@@ -374,15 +397,7 @@ bucket_pass_kernel(const __grid_constant__ BucketParams P) {
       tt[k] = (b < nb) ? s_tot[b] : 0;
       tsum += tt[k];
     }
-    s_scan[threadIdx.x] = tsum;
-    __syncthreads();
-    for (int off = 1; off < kBucketThreads; off <<= 1) {
-      int32_t add = (threadIdx.x >= off) ? s_scan[threadIdx.x - off] : 0;
-      __syncthreads();
-      s_scan[threadIdx.x] += add;
-      __syncthreads();
-    }
-    int32_t run = s_scan[threadIdx.x] - tsum;
+    int32_t run = block_excl_scan(tsum, s_scan, nullptr);
 #pragma unroll
     for (int k = 0; k < kBinsPerThread; ++k) {
       const int b = threadIdx.x * kBinsPerThread + k;

@@ -55,8 +55,9 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 // 128-bit streaming loads/stores (read-once data: bypass L1 allocation).
 __device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
   float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  // not volatile: a pure load of read-only data, free to be hoisted and batched
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ float4 ld_f4(const float4* p) { return *p; }
@@ -66,7 +67,7 @@ __device__ __forceinline__ void st_na_f4(float4* p, const float4& v) {
 }
 __device__ __forceinline__ int64_t ld_nc_i64(const int64_t* p) {
   int64_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(r) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(r) : "l"(p));
   return r;
 }
 

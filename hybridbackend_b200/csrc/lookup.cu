@@ -88,14 +88,22 @@ __device__ __forceinline__ void load_rows(const LookupFeat& F, int cid, int64_t 
   const int groups = kLookupThreads >> F.log2g;
   const int g = threadIdx.x >> F.log2g;
   const int bag0 = (cid - F.cta_begin) * groups * kBagsPerGroup;
+  // all id loads first (independent, in flight together), then the row math
+  int64_t raw[kBagsPerGroup];
 #pragma unroll
   for (int u = 0; u < kBagsPerGroup; ++u) {
     const int b = bag0 + u * groups + g;
-    r[u] = -2;
-    if (b < F.nbags) {
-      r[u] = row_of(F, b);
-      if ((uint64_t)r[u] >= (uint64_t)F.rows) { oob = true; r[u] = -1; }
-    }
+    const int bb = b < F.nbags ? b : 0;
+    raw[u] = (F.idx32 != nullptr) ? (int64_t)F.idx32[bb] : ld_nc_i64(F.ids + bb);
+  }
+#pragma unroll
+  for (int u = 0; u < kBagsPerGroup; ++u) {
+    const int b = bag0 + u * groups + g;
+    int64_t row = (F.idx32 != nullptr) ? raw[u] : local_row(raw[u], F);
+    const bool bad = (uint64_t)row >= (uint64_t)F.rows;
+    if (b >= F.nbags) row = -2;
+    else if (bad) { oob = true; row = -1; }
+    r[u] = row;
   }
 }
 
@@ -177,11 +185,15 @@ lookup_fwd_kernel(const __grid_constant__ LookupParams P) {
           int64_t rr[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            rr[k] = -1;
-            if (p + k < e) {
-              rr[k] = row_of(F, p + k);
-              if ((uint64_t)rr[k] >= (uint64_t)F.rows) { oob = true; rr[k] = -1; }
-            }
+            const int64_t pp = (p + k < e) ? p + k : p;
+            rr[k] = (F.idx32 != nullptr) ? (int64_t)F.idx32[pp] : ld_nc_i64(F.ids + pp);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (F.idx32 == nullptr) rr[k] = local_row(rr[k], F);
+            const bool bad = (uint64_t)rr[k] >= (uint64_t)F.rows;
+            if (p + k >= e) rr[k] = -1;
+            else if (bad) { oob = true; rr[k] = -1; }
           }
           float4 x[4][V];
 #pragma unroll

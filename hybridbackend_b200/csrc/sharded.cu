@@ -242,13 +242,19 @@ __global__ void __launch_bounds__(256) sh_owner_gather_kernel(const __grid_const
     int q[kShRowsPerGroup];
     int dstrow[kShRowsPerGroup];
     bool ok[kShRowsPerGroup];
+    int64_t idv[kShRowsPerGroup];
+#pragma unroll
+    for (int u = 0; u < kShRowsPerGroup; ++u) {  // all id loads in flight together
+      const int p = p0 + u * groups + g;
+      idv[u] = ids_in[p < total ? p : p0];
+    }
 #pragma unroll
     for (int u = 0; u < kShRowsPerGroup; ++u) {
       const int p = p0 + u * groups + g;
       ok[u] = p < total;
       row[u] = -1; q[u] = 0; dstrow[u] = 0;
       if (ok[u]) {
-        const int64_t id = ids_in[p];
+        const int64_t id = idv[u];
         int64_t r = -1;
         if (id >= 0) r = P.div_shift >= 0 ? (int64_t)((uint64_t)id >> P.div_shift) : id / P.world;
         if ((uint64_t)r >= (uint64_t)F.shard_rows) { oob = true; r = -1; }
@@ -310,18 +316,25 @@ __global__ void __launch_bounds__(256) sh_push_grads_kernel(const __grid_constan
     int bag[kShRowsPerGroup], r[kShRowsPerGroup], drow[kShRowsPerGroup];
     float sc[kShRowsPerGroup];
     bool ok[kShRowsPerGroup];
+    int jv[kShRowsPerGroup];
+#pragma unroll
+    for (int u = 0; u < kShRowsPerGroup; ++u) {  // independent loads first
+      const int p = p0 + u * groups + g;
+      const int pp = p < F.nnz ? p : p0;
+      jv[u] = F.part_idx[pp];
+      bag[u] = F.offsets != nullptr ? F.bag_of_pos[pp] : pp;
+    }
 #pragma unroll
     for (int u = 0; u < kShRowsPerGroup; ++u) {
       const int p = p0 + u * groups + g;
       ok[u] = p < F.nnz;
-      bag[u] = 0; r[u] = 0; drow[u] = 0; sc[u] = 1.0f;
+      r[u] = 0; drow[u] = 0; sc[u] = 1.0f;
       if (ok[u]) {
-        bag[u] = F.offsets != nullptr ? F.bag_of_pos[p] : p;
         if (scaled) {
           const int64_t c = F.offsets[bag[u] + 1] - F.offsets[bag[u]];
           sc[u] = (F.combiner == HB_MEAN) ? (float)c : __fsqrt_rn((float)c);
         }
-        const int j = F.part_idx[p];
+        const int j = jv[u];
         int rr = 0;
         while (rr + 1 < P.world && m.send_off[rr + 1] <= j) ++rr;
         r[u] = rr;

@@ -164,8 +164,13 @@ __device__ __forceinline__ bool apply_row(const UpdParams& P, const UpdFeat& F, 
   return apply_rows<V, 1, OPT>(P, F, 1u, k1, g1, col, act);
 }
 
-// smem per CTA: groups * (2*V*G float4 partials + 2 keys + 1 flag)
-template <int V, int C, int OPT>
+// A warp owns 32 consecutive sorted entries (lane e holds key/bag of entry e: one
+// coalesced load each); the run structure of the warp tile is a pair of ballot
+// masks.  Each of the 32/G groups walks its G consecutive entries in sub-batches
+// of SB: the gradient rows AND the table/slot rows of the runs ending in the
+// sub-batch are loaded together (one memory round trip), summed in position
+// order, and applied.  smem per CTA: groups * (2*V*G float4 partials + 2 keys + flag).
+template <int V, int OPT>
 __global__ void __launch_bounds__(kUpdThreads, (V == 1 ? 3 : 1))
 sparse_update_kernel(const __grid_constant__ UpdParams P) {
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -194,58 +199,116 @@ sparse_update_kernel(const __grid_constant__ UpdParams P) {
     act[v] = col[v] < dim;
   }
   bool oob = false;
-
-  const int64_t e0 = ((int64_t)st * groups + g) * C;
-  const int cnt = (int)max((int64_t)0, min((int64_t)C, (int64_t)n - e0));
   int flag = 0;
 
+  // ---- warp tile: 32 entries, lane e <-> entry e -------------------------------
+  const unsigned lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int64_t w0 = ((int64_t)st * (kUpdThreads / 32) + warp) * 32;  // first entry of the warp
+  const int wcnt = (int)max((int64_t)0, min((int64_t)32, (int64_t)n - w0));
+  uint32_t my_key = 0xFFFFFFFFu;
+  int32_t my_bag = 0;
+  if ((int)lane < wcnt) { my_key = F.keys[w0 + lane]; my_bag = F.bags[w0 + lane]; }
+  // neighbours of the warp tile
+  uint32_t edge_key = 0;
+  bool edge_has = false;
+  if (lane == 0 && wcnt > 0 && w0 > 0) { edge_key = F.keys[w0 - 1]; edge_has = true; }
+  if (lane == 31 && wcnt == 32 && w0 + 32 < n) { edge_key = F.keys[w0 + 32]; edge_has = true; }
+  float my_scale = 1.0f;
+  const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
+  if (scaled && (int)lane < wcnt) {
+    const int64_t c = F.offsets[my_bag + 1] - F.offsets[my_bag];
+    my_scale = (F.combiner == HB_MEAN) ? (float)c : __fsqrt_rn((float)c);
+  }
+  // same_prev bit e: entry e has the same key as entry e-1 (globally)
+  const uint32_t up_key = __shfl_up_sync(0xffffffffu, my_key, 1);
+  bool sp = false;
+  if ((int)lane < wcnt) sp = (lane == 0) ? (edge_has && edge_key == my_key) : (up_key == my_key);
+  const unsigned same_prev = __ballot_sync(0xffffffffu, sp);
+  // does the run of the warp's last entry continue in the next warp tile?
+  const unsigned cont_next = __ballot_sync(0xffffffffu, lane == 31 && edge_has && edge_key == my_key);
+  const bool warp_open_right = cont_next != 0;
+
+  // ---- group tile: C = G consecutive entries of the warp tile --------------------
+  constexpr int SB = (V == 1) ? 4 : (V == 2 ? 2 : 1);
+  const int gw = (lane >> log2g);     // group index inside the warp
+  const int c0 = gw * G;              // first warp-entry of my group
+  const int cnt = max(0, min(G, wcnt - c0));
+  float4* my_part = s_part + (size_t)g * 2 * V * G;
   if (cnt > 0) {
-    const bool has_prev = e0 > 0;
-    const bool has_next = e0 + cnt < n;
-    const uint32_t pk = has_prev ? F.keys[e0 - 1] : 0u;
-    const uint32_t nk = has_next ? F.keys[e0 + cnt] : 0u;
-    const uint32_t k_first = F.keys[e0];
-    const bool first_open_left = has_prev && pk == k_first;
-    const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
+    const bool first_open_left = (same_prev >> c0) & 1u;
     bool seen_tail = false;
     float4 carry[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) carry[v] = f4_zero();
-    float4* my_part = s_part + (size_t)g * 2 * V * G;
-    constexpr int SB = (C < 4) ? C : 4;  // entries whose loads are batched
 #pragma unroll 1
     for (int j0 = 0; j0 < cnt; j0 += SB) {
-      // keys of the sub-batch and its two neighbours; bags
       uint32_t k[SB];
-      int32_t bg[SB];
-#pragma unroll
-      for (int i = 0; i < SB; ++i) {
-        k[i] = 0xFFFFFFFFu;
-        bg[i] = 0;
-        if (j0 + i < cnt) { k[i] = F.keys[e0 + j0 + i]; bg[i] = F.bags[e0 + j0 + i]; }
-      }
-      const uint32_t k_before = (j0 > 0) ? F.keys[e0 + j0 - 1] : 0u;
-      const uint32_t k_after = (j0 + SB < cnt) ? F.keys[e0 + j0 + SB] : 0u;
-      // bag scale (mean: count, sqrtn: sqrt(count)) -- divided as the oracle does
+      bool valid[SB], head[SB], is_apply[SB];
+      int part_slot[SB];  // -1 none, 0 first-open partial, 1 last-open partial
+      int part_flag[SB];
+      unsigned apply_mask = 0;
+      float4 gv[SB][V];
       float sc[SB];
 #pragma unroll
       for (int i = 0; i < SB; ++i) {
-        sc[i] = 1.0f;
-        if (scaled && j0 + i < cnt) {
-          const int64_t c = F.offsets[bg[i] + 1] - F.offsets[bg[i]];
-          sc[i] = (F.combiner == HB_MEAN) ? (float)c : __fsqrt_rn((float)c);
+        const int e = c0 + j0 + i;                 // entry index inside the warp tile
+        valid[i] = (j0 + i) < cnt;
+        const int src = valid[i] ? e : c0;
+        k[i] = __shfl_sync(0xffffffffu, my_key, src);
+        const int32_t bag = __shfl_sync(0xffffffffu, my_bag, src);
+        sc[i] = __shfl_sync(0xffffffffu, my_scale, src);
+        head[i] = !((same_prev >> src) & 1u);
+        is_apply[i] = false;
+        part_slot[i] = -1;
+        part_flag[i] = 0;
+        if (valid[i]) {
+          const bool last = (j0 + i == cnt - 1);
+          // tail: the next entry (inside the warp tile, or beyond it) starts a new run
+          bool next_same;
+          if (e + 1 < wcnt) next_same = (same_prev >> (e + 1)) & 1u;
+          else next_same = warp_open_right;        // e is the warp tile's last entry
+          const bool tail = !next_same || last;
+          if (tail) {
+            const bool ol = first_open_left && !seen_tail;
+            const bool orr = last && next_same;
+            if (!ol && !orr) { is_apply[i] = true; apply_mask |= 1u << i; }
+            else if (ol) { part_slot[i] = 0; part_flag[i] = kFirstOpen | (orr ? kBoth : 0); }
+            else { part_slot[i] = 1; part_flag[i] = kLastOpen; }
+            seen_tail = true;
+          }
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            gv[i][v] = f4_zero();
+            if (act[v])
+              gv[i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
+                  F.grad + (int64_t)bag * F.grad_stride + col[v]));
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) gv[i][v] = f4_zero();
         }
       }
-      float4 gv[SB][V];
+      // table / slot rows of the runs that end (closed) in this sub-batch: issued
+      // right behind the gradient loads, consumed after the sums
+      bool ok[SB];
+      float4 w[SB][V], s0[SB][V], s1[SB][V];
 #pragma unroll
-      for (int i = 0; i < SB; ++i)
+      for (int i = 0; i < SB; ++i) {
+        ok[i] = is_apply[i];
+        if (ok[i] && k[i] == 0xFFFFFFFFu) ok[i] = false;                      // padding entry
+        if (ok[i] && (uint64_t)k[i] >= (uint64_t)F.rows) { ok[i] = false; oob = true; }
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          gv[i][v] = f4_zero();
-          if (j0 + i < cnt && act[v])
-            gv[i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
-                F.grad + (int64_t)bg[i] * F.grad_stride + col[v]));
+          w[i][v] = s0[i][v] = s1[i][v] = f4_zero();
+          if (ok[i] && act[v]) {
+            const int64_t o = (int64_t)k[i] * dim + col[v];
+            w[i][v] = *reinterpret_cast<const float4*>(F.table + o);
+            if constexpr (OPT != HB_OPT_SGD) s0[i][v] = *reinterpret_cast<const float4*>(F.slot0 + o);
+            if constexpr (OPT == HB_OPT_LAZY_ADAM) s1[i][v] = *reinterpret_cast<const float4*>(F.slot1 + o);
+          }
         }
+      }
       if (scaled) {
 #pragma unroll
         for (int i = 0; i < SB; ++i)
@@ -257,45 +320,35 @@ sparse_update_kernel(const __grid_constant__ UpdParams P) {
       // segmented inclusive sums, in position order
 #pragma unroll
       for (int i = 0; i < SB; ++i) {
-        if (j0 + i < cnt) {
-          const bool head = (i == 0) ? (j0 == 0 || k[0] != k_before) : (k[i] != k[i - 1]);
-          if (!head) {
+        if (valid[i]) {
+          const bool cont = (j0 + i == 0) ? false : !head[i];  // continues a run of THIS group tile
+          if (cont) {
 #pragma unroll
             for (int v = 0; v < V; ++v)
               gv[i][v] = f4_add_rn(i == 0 ? carry[v] : gv[i > 0 ? i - 1 : 0][v], gv[i][v]);
           }
         }
       }
-      // classify run ends
-      unsigned apply_mask = 0;
+      // run ends: apply or park the partial sum
 #pragma unroll
       for (int i = 0; i < SB; ++i) {
-        const int j = j0 + i;
-        if (j < cnt) {
-          const bool last = (j == cnt - 1);
-          const uint32_t knext = (i + 1 < SB) ? k[i + 1 < SB ? i + 1 : i] : k_after;
-          const bool tail = last || (k[i] != knext);
-          if (tail) {
-            const bool ol = first_open_left && !seen_tail;
-            const bool orr = last && has_next && nk == k[i];
-            if (!ol && !orr) {
-              apply_mask |= 1u << i;
-            } else if (ol) {
+        if (ok[i]) {
 #pragma unroll
-              for (int v = 0; v < V; ++v) my_part[(0 * V + v) * G + l] = gv[i][v];
-              if (l == 0) s_key[g * 2 + 0] = k[i];
-              flag |= kFirstOpen | (orr ? kBoth : 0);
-            } else {
-#pragma unroll
-              for (int v = 0; v < V; ++v) my_part[(1 * V + v) * G + l] = gv[i][v];
-              if (l == 0) s_key[g * 2 + 1] = k[i];
-              flag |= kLastOpen;
+          for (int v = 0; v < V; ++v)
+            if (act[v]) {
+              const int64_t o = (int64_t)k[i] * dim + col[v];
+              opt_step4<OPT>(P, w[i][v], s0[i][v], s1[i][v], gv[i][v]);
+              *reinterpret_cast<float4*>(F.table + o) = w[i][v];
+              if constexpr (OPT != HB_OPT_SGD) *reinterpret_cast<float4*>(F.slot0 + o) = s0[i][v];
+              if constexpr (OPT == HB_OPT_LAZY_ADAM) *reinterpret_cast<float4*>(F.slot1 + o) = s1[i][v];
             }
-            seen_tail = true;
-          }
+        } else if (part_slot[i] >= 0) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) my_part[(part_slot[i] * V + v) * G + l] = gv[i][v];
+          if (l == 0) s_key[g * 2 + part_slot[i]] = k[i];
+          flag |= part_flag[i];
         }
       }
-      if (!apply_rows<V, SB, OPT>(P, F, apply_mask, k, gv, col, act)) oob = true;
 #pragma unroll
       for (int v = 0; v < V; ++v) carry[v] = gv[SB - 1][v];
     }
@@ -472,7 +525,6 @@ static void upd_shape(int dim, int* log2g, int* v) {
 constexpr int kRadixBits = 9;
 constexpr int kRadixBins = 1 << kRadixBits;
 
-static int tile_c(int V) { return V == 1 ? 8 : (V == 2 ? 4 : 2); }
 
 // per-feature workspace layout
 struct UpdLayout {
@@ -489,9 +541,8 @@ static UpdLayout upd_layout(const hbUpdateFeature& f, size_t base) {
   L.valsA = take(4 * n); L.valsB = take(4 * n);
   L.bagmap = take(f.offsets ? 4 * n : 0);
   upd_shape(f.dim, &L.log2g, &L.V);
-  L.C = tile_c(L.V);
-  const int groups = kUpdThreads >> L.log2g;
-  const int64_t per_st = (int64_t)groups * L.C;
+  L.C = 1 << L.log2g;  // entries per group: a warp owns 32 entries, a CTA 256
+  const int64_t per_st = kUpdThreads;
   L.nst = (int)((f.nnz + per_st - 1) / per_st);
   L.st_part = take((size_t)L.nst * 2 * f.dim * 4);
   L.st_key = take((size_t)L.nst * 2 * 4);
@@ -504,16 +555,16 @@ static UpdLayout upd_layout(const hbUpdateFeature& f, size_t base) {
   return L;
 }
 
-template <int V, int C, int OPT>
+template <int V, int OPT>
 static int launch_update_opt(const UpdParams& P, const UpdParams& X, cudaStream_t stream) {
   // smem: groups*(2*V*G*16 + 12) with groups*G == 256
   const size_t smem = (size_t)2 * V * kUpdThreads * 16 + (size_t)kUpdThreads * 12;
   if (smem > 48 * 1024)
-    HB_CUDA_OK(cudaFuncSetAttribute(sparse_update_kernel<V, C, OPT>,
+    HB_CUDA_OK(cudaFuncSetAttribute(sparse_update_kernel<V, OPT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (P.total_ctas > 0) {
     KernelScope ks(HB_K_SPARSE_UPDATE, stream);
-    sparse_update_kernel<V, C, OPT><<<P.total_ctas, kUpdThreads, smem, stream>>>(P);
+    sparse_update_kernel<V, OPT><<<P.total_ctas, kUpdThreads, smem, stream>>>(P);
   }
   HB_CUDA_OK(cudaGetLastError());
   if (X.total_ctas > 0) {
@@ -524,12 +575,12 @@ static int launch_update_opt(const UpdParams& P, const UpdParams& X, cudaStream_
   return HB_OK;
 }
 
-template <int V, int C>
+template <int V>
 static int launch_update(const UpdParams& P, const UpdParams& X, cudaStream_t stream) {
   switch (P.opt) {
-    case HB_OPT_ADAGRAD: return launch_update_opt<V, C, HB_OPT_ADAGRAD>(P, X, stream);
-    case HB_OPT_LAZY_ADAM: return launch_update_opt<V, C, HB_OPT_LAZY_ADAM>(P, X, stream);
-    default: return launch_update_opt<V, C, HB_OPT_SGD>(P, X, stream);
+    case HB_OPT_ADAGRAD: return launch_update_opt<V, HB_OPT_ADAGRAD>(P, X, stream);
+    case HB_OPT_LAZY_ADAM: return launch_update_opt<V, HB_OPT_LAZY_ADAM>(P, X, stream);
+    default: return launch_update_opt<V, HB_OPT_SGD>(P, X, stream);
   }
 }
 
@@ -731,10 +782,10 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
       for (int k = 0; k < X.nfeats; ++k) X.f[k].cta_begin = fix_begin[k];
       X.total_ctas = fix_ctas;
       switch (V) {
-        case 1: rc = launch_update<1, 8>(U, X, stream); break;
-        case 2: rc = launch_update<2, 4>(U, X, stream); break;
-        case 4: rc = launch_update<4, 2>(U, X, stream); break;
-        default: rc = launch_update<8, 2>(U, X, stream); break;
+        case 1: rc = launch_update<1>(U, X, stream); break;
+        case 2: rc = launch_update<2>(U, X, stream); break;
+        case 4: rc = launch_update<4>(U, X, stream); break;
+        default: rc = launch_update<8>(U, X, stream); break;
       }
       if (rc != HB_OK) return rc;
     }

@@ -55,13 +55,18 @@ def _spawn(fn_name, world=2):
   procs = [ctx.Process(target=_worker, args=(r, world, port, fn_name, q)) for r in range(world)]
   for p in procs:
     p.start()
+  import queue as _queue
   res = []
   try:
     for _ in range(world):
-      res.append(q.get(timeout=300))
+      try:
+        res.append(q.get(timeout=150 if not res else 40))
+      except _queue.Empty:
+        res.append((-1, 'a rank never reported (hung in a kernel or crashed hard)'))
+        break
   finally:
     for p in procs:
-      p.join(timeout=30)
+      p.join(timeout=10)
       if p.is_alive():
         p.kill()
   bad = [r for r in res if r[1] != 'ok']
@@ -129,8 +134,26 @@ def test_alltoallv_vs_oracle_2gpu():
   _spawn('_alltoallv_random')
 
 
+class _Soft:
+  """Collects assertion failures instead of raising mid-protocol: a rank that
+  stops early would leave its peer spinning on a flag inside a kernel."""
+
+  def __init__(self):
+    self.errors = []
+
+  def allclose(self, got, exp, msg, **kw):
+    try:
+      np.testing.assert_allclose(got, exp, err_msg=msg, **kw)
+    except AssertionError as e:
+      self.errors.append(str(e)[:600])
+
+  def done(self):
+    assert not self.errors, '\n'.join(self.errors)
+
+
 def _sharded_lookup(rank, world, hb, o):
   dev = torch.device('cuda', rank)
+  soft = _Soft()
   rng = np.random.RandomState(11)  # shared
   sizes = [1003, 40000, 2, 250000]   # 2 rows <= W -> "small" (replicated) table
   D, B = 32, 3000
@@ -165,15 +188,14 @@ def _sharded_lookup(rank, world, hb, o):
   for step in range(2):
     mine = feats_all[rank]
     out = gl.forward([torch.from_numpy(f[0]).to(dev) for f in mine],
-                     [torch.from_numpy(f[1]).to(dev) if f[1] is not None else None for f in mine],
-                     check=True).cpu().numpy()
+                     [torch.from_numpy(f[1]).to(dev) if f[1] is not None else None for f in mine]
+                     ).cpu().numpy()
     for j in range(len(sizes)):
       ids, off = mine[j]
       offs = off if off is not None else np.arange(len(ids) + 1, dtype=np.int64)
       exp = o.embedding_lookup_sparse(ref_tables[j], ids, offs, comb[j])
-      np.testing.assert_allclose(out[:, j * D:(j + 1) * D], exp, rtol=1e-5, atol=1e-7,
-                                 err_msg=f'step {step} feature {j}')
-    gl.backward_update(torch.from_numpy(grads[rank]).to(dev), opt, check=True)
+      soft.allclose(out[:, j * D:(j + 1) * D], exp, f'step {step} feature {j}', rtol=1e-5, atol=1e-7)
+    gl.backward_update(torch.from_numpy(grads[rank]).to(dev), opt)
     # oracle: sharded tables get the SUM over ranks of the per-rank gradients
     # (training/gradient.py:216-217), applied once per step and unique row
     for j in range(len(sizes)):
@@ -190,12 +212,18 @@ def _sharded_lookup(rank, world, hb, o):
       o.sparse_apply_adagrad(ref_tables[j], ref_acc[j], np.concatenate(rows), np.concatenate(rgs), 0.05)
     for j in sh:
       got = tables[j].weight.cpu().numpy()
-      np.testing.assert_allclose(got, ref_tables[j][rank::world], rtol=2e-5, atol=1e-6,
-                                 err_msg=f'step {step} table {j}')
+      soft.allclose(got, ref_tables[j][rank::world], f'step {step} table {j}', rtol=2e-5, atol=1e-6)
     # small (replicated) table: gradients of all ranks all-gathered, replicas identical
     got = tables[2].weight.cpu().numpy()
-    np.testing.assert_allclose(got, ref_tables[2], rtol=2e-5, atol=1e-6)
+    soft.allclose(got, ref_tables[2], f'step {step} replicated table', rtol=2e-5, atol=1e-6)
+  torch.cuda.synchronize()
+  dist.barrier()
+  try:
+    hb._util.check_status(dev)
+  except Exception as e:  # pylint: disable=broad-except
+    soft.errors.append(f'status word: {e}')
   coll.close()
+  soft.done()
 
 
 def test_sharded_group_lookup_2gpu():
