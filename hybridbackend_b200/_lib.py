@@ -104,7 +104,7 @@ SYMBOLS = [
     'hbProfileEnable', 'hbProfileReset', 'hbProfileGet', 'hbKernelName',
     'hbPartitionWorkspaceBytes', 'hbPartitionByModuloN', 'hbPartitionByDualModuloN',
     'hbGroupLookupForward', 'hbGroupSparseUpdateWorkspaceBytes',
-    'hbGroupLookupBackwardUpdate', 'hbCastN', 'hbCacheLookup',
+    'hbGroupLookupBackwardUpdate', 'hbGroupSparseSort', 'hbGroupSparseApply', 'hbCastN', 'hbCacheLookup',
     'hbCommCreate', 'hbCommConnect', 'hbCommDestroy', 'hbCommRank', 'hbCommWorldSize',
     'hbCommWindow', 'hbCommWindowBytes', 'hbCommBarrier',
     'hbAlltoallvNSizes', 'hbAlltoallvN',

@@ -67,6 +67,9 @@ def check_status(device, clear=True):
     raise IndexError('embedding id out of range for its table')
   if v & _lib.STATUS_BAD_OFFSETS:
     raise ValueError('bag offsets are not non-decreasing / within nnz')
+  if v & 8:
+    raise RuntimeError('timed out waiting for a peer rank (a rank crashed or ranks issued '
+                       'different collective sequences)')
   if v & _lib.STATUS_WINDOW_OVERFLOW:
     raise RuntimeError('sharded lookup receive window overflow (raise capacity_factor)')
   return v

@@ -38,8 +38,7 @@ __global__ void barrier_kernel(PeerPtrs peers, int me, int world, uint32_t epoch
     Control* remote = reinterpret_cast<Control*>(peers.p[q]);
     st_release_sys_u32(&remote->barrier_flags[me], epoch);
     Control* mine = reinterpret_cast<Control*>(peers.p[me]);
-    while ((int32_t)(ld_acquire_sys_u32(&mine->barrier_flags[q]) - epoch) < 0) {
-    }
+    wait_flag(&mine->barrier_flags[q], epoch);
   }
 }
 
@@ -68,8 +67,7 @@ a2a_sizes_kernel(const __grid_constant__ SizesParams P, PeerPtrs peers, int me, 
   if ((int)threadIdx.x < world) {
     Control* remote = reinterpret_cast<Control*>(peers.p[threadIdx.x]);
     st_release_sys_u32(&remote->sizes_flags[parity][me], call);
-    while ((int32_t)(ld_acquire_sys_u32(&mine->sizes_flags[parity][threadIdx.x]) - call) < 0) {
-    }
+    wait_flag(&mine->sizes_flags[parity][threadIdx.x], call);
   }
   __syncthreads();
   // 2. snapshot the matrix
@@ -239,8 +237,7 @@ a2a_copyout_kernel(const __grid_constant__ PullParams P, PeerPtrs peers, int me,
                    int slot, int half, uint64_t window_off, uint64_t half_bytes, uint32_t call) {
   Control* mine = reinterpret_cast<Control*>(peers.p[me]);
   if ((int)threadIdx.x < world) {
-    while ((int32_t)(ld_acquire_sys_u32(&mine->data_flags[half][threadIdx.x]) - call) < 0) {
-    }
+    wait_flag(&mine->data_flags[half][threadIdx.x], call);
   }
   __syncthreads();
   const Snapshot* S = &mine->snap[slot];

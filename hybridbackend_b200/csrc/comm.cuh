@@ -71,9 +71,8 @@ static inline PeerPtrs peer_ptrs(const hbComm* c) {
 }
 
 // spin until flag (epoch-valued, monotonically increasing) reaches `epoch`
-__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch) {
-  while ((int32_t)(ld_acquire_sys_u32(flag) - epoch) < 0) {
-  }
+__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t epoch) {
+  return spin_until(flag, epoch);
 }
 
 }  // namespace hb

@@ -94,11 +94,32 @@ struct WaitSpec {
   int32_t n;
 };
 
-__device__ __forceinline__ void wait_spec(const WaitSpec& w) {
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Bounded spin on an epoch flag: a peer that never arrives (crashed rank, ranks
+// issuing different op sequences) must not hang the GPU forever -- after
+// kSpinTimeoutNs the waiter gives up and raises HB_STATUS_PEER_TIMEOUT (the
+// reference relies on an NCCL watchdog thread for the same failure,
+// nccl/nccl_create.cc:104-117).  Returns false on timeout.
+constexpr uint64_t kSpinTimeoutNs = 20ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ bool spin_until(const uint32_t* flag, uint32_t epoch) {
+  if ((int32_t)(ld_acquire_sys_u32(flag) - epoch) >= 0) return true;
+  const uint64_t t0 = globaltimer_ns();
+  while ((int32_t)(ld_acquire_sys_u32(flag) - epoch) < 0) {
+    if (globaltimer_ns() - t0 > kSpinTimeoutNs) return false;
+  }
+  return true;
+}
+
+__device__ __forceinline__ void wait_spec(const WaitSpec& w, int32_t* status = nullptr) {
   if (w.flags != nullptr) {
     if ((int)threadIdx.x < w.n) {
-      while ((int32_t)(ld_acquire_sys_u32(w.flags + threadIdx.x) - w.epoch) < 0) {
-      }
+      if (!spin_until(w.flags + threadIdx.x, w.epoch) && status != nullptr)
+        atomicOr(status, HB_STATUS_PEER_TIMEOUT);
     }
     __syncthreads();
   }
@@ -119,6 +140,6 @@ int lookup_forward_run(int n, const hbLookupFeature* feats, const int32_t* const
 // sparse_update.cu
 int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* opt, void* ws,
                       size_t ws_bytes, int32_t* d_status, cudaStream_t stream,
-                      const WaitSpec* wait, const int32_t* const* n_dev);
+                      const WaitSpec* wait, const int32_t* const* n_dev, int phases = 3);
 
 }  // namespace hb

@@ -114,7 +114,7 @@ __device__ __forceinline__ void load_rows(const LookupFeat& F, int cid, int64_t 
 template <int V, bool COH>
 __global__ void __launch_bounds__(kLookupThreads)
 lookup_fwd_kernel(const __grid_constant__ LookupParams P) {
-  wait_spec(P.wait);
+  wait_spec(P.wait, P.status);
   bool oob = false;
   bool bad_off = false;
   int cid = blockIdx.x;

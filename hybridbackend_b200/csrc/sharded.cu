@@ -110,7 +110,8 @@ __device__ __forceinline__ void signal_all_peers(const ShParams& P, int phase, i
 
 __device__ __forceinline__ void wait_all_peers(const ShParams& P, int phase) {
   if ((int)threadIdx.x < P.world)
-    wait_flag(&ctl(P, P.me)->plan_flags[phase][threadIdx.x], P.epoch);
+    if (!wait_flag(&ctl(P, P.me)->plan_flags[phase][threadIdx.x], P.epoch))
+      raise_status(P.status, HB_STATUS_PEER_TIMEOUT);
   __syncthreads();
 }
 
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(256) sh_exchange_kernel(const __grid_constant_
   __syncthreads();
   if ((int)threadIdx.x < W) {
     st_release_sys_u32(&ctl(P, threadIdx.x)->plan_flags[0][me], P.epoch);
-    wait_flag(&mine->plan_flags[0][threadIdx.x], P.epoch);
+    if (!wait_flag(&mine->plan_flags[0][threadIdx.x], P.epoch))
+      raise_status(P.status, HB_STATUS_PEER_TIMEOUT);
   }
   __syncthreads();
   auto S = [&](int q, int f, int r) -> int32_t {

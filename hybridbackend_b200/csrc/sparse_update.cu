@@ -174,7 +174,7 @@ template <int V, int OPT>
 __global__ void __launch_bounds__(kUpdThreads, (V == 1 ? 3 : 1))
 sparse_update_kernel(const __grid_constant__ UpdParams P) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  wait_spec(P.wait);
+  wait_spec(P.wait, P.status);
   const int fi = find_upd_feat(P, blockIdx.x);
   const UpdFeat& F = P.f[fi];
   const int st = blockIdx.x - F.cta_begin;
@@ -235,14 +235,16 @@ sparse_update_kernel(const __grid_constant__ UpdParams P) {
   const int c0 = gw * G;              // first warp-entry of my group
   const int cnt = max(0, min(G, wcnt - c0));
   float4* my_part = s_part + (size_t)g * 2 * V * G;
-  if (cnt > 0) {
+  if (wcnt > 0) {  // warp-uniform: every lane takes part in the shuffles below
     const bool first_open_left = (same_prev >> c0) & 1u;
     bool seen_tail = false;
     float4 carry[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) carry[v] = f4_zero();
+    // trip count G/SB is the same for every group of the warp (groups with fewer
+    // valid entries run predicated-off iterations)
 #pragma unroll 1
-    for (int j0 = 0; j0 < cnt; j0 += SB) {
+    for (int j0 = 0; j0 < G; j0 += SB) {
       uint32_t k[SB];
       bool valid[SB], head[SB], is_apply[SB];
       int part_slot[SB];  // -1 none, 0 first-open partial, 1 last-open partial
@@ -417,9 +419,12 @@ sparse_update_kernel(const __grid_constant__ UpdParams P) {
   if (threadIdx.x == 0) F.st_flag[st] = s_stflag;
 }
 
-// Finish rows that span super-tiles: group per super-tile that STARTS a chain.
-// The chain is walked 8 super-tiles at a time: flags and partial sums of the
-// next 8 are loaded speculatively in one round trip, then added in order.
+// Finish rows that span super-tiles (hot keys): one WARP per super-tile that
+// starts a chain.  Per round the warp reads the flags of the next 32 super-tiles
+// with one coalesced load and finds the chain end with a ballot; its 32/G groups
+// then sum the partial rows t+gi, t+gi+ng, ... (independent loads), and the group
+// sums are combined in a fixed order with shuffles.  Order of addition is a fixed
+// function of the chain length => deterministic.
 template <int V, int OPT>
 __global__ void __launch_bounds__(kUpdThreads)
 sparse_update_fixup_kernel(const __grid_constant__ UpdParams P) {
@@ -427,12 +432,13 @@ sparse_update_fixup_kernel(const __grid_constant__ UpdParams P) {
   const UpdFeat& F = P.f[fi];
   const int log2g = F.log2g;
   const int G = 1 << log2g;
-  const int groups = kUpdThreads >> log2g;
-  const int g = threadIdx.x >> log2g;
-  const int l = threadIdx.x & (G - 1);
+  const int ng = 32 >> log2g;            // groups per warp
+  const unsigned lane = lane_id();
+  const int gi = lane >> log2g;          // my group inside the warp
+  const int l = lane & (G - 1);
   const int dim = F.dim;
-  const int st = (blockIdx.x - F.cta_begin) * groups + g;
-  if (st >= F.nst) return;
+  const int st = (blockIdx.x - F.cta_begin) * (kUpdThreads / 32) + (threadIdx.x >> 5);
+  if (st >= F.nst) return;               // warp-uniform
   if (!(F.st_flag[st] & kLastOpen)) return;
   int col[V];
   bool act[V];
@@ -441,42 +447,63 @@ sparse_update_fixup_kernel(const __grid_constant__ UpdParams P) {
     col[v] = ((v << log2g) + l) * 4;
     act[v] = col[v] < dim;
   }
+  // group 0 starts from the chain head's partial, the others from zero
   float4 acc[V];
 #pragma unroll
   for (int v = 0; v < V; ++v)
-    acc[v] = act[v] ? *reinterpret_cast<const float4*>(F.st_part + ((size_t)st * 2 + 1) * dim + col[v])
-                    : f4_zero();
+    acc[v] = (gi == 0 && act[v])
+                 ? *reinterpret_cast<const float4*>(F.st_part + ((size_t)st * 2 + 1) * dim + col[v])
+                 : f4_zero();
   const uint32_t key = F.st_key[(size_t)st * 2 + 1];
-  constexpr int kAhead = 8;
   int t = st + 1;
   bool done = false;
   while (!done && t < F.nst) {
-    int fl[kAhead];
-    float4 x[kAhead][V];
+    // flags of super-tiles t .. t+31
+    const int fl = (t + (int)lane < F.nst) ? F.st_flag[t + lane] : 0;
+    const unsigned is_first = __ballot_sync(0xffffffffu, (fl & kFirstOpen) != 0);
+    const unsigned is_both = __ballot_sync(0xffffffffu, (fl & kBoth) != 0);
+    // chain covers tiles while FirstOpen; it ends after the first one without Both
+    const unsigned stop_a = ~is_first;            // tile does not continue the chain at all
+    const unsigned stop_b = is_first & ~is_both;  // last tile of the chain (included)
+    int m;                                        // number of tiles of this round to add
+    const int pa = stop_a ? __ffs(stop_a) - 1 : 32;
+    const int pb = stop_b ? __ffs(stop_b) - 1 : 32;
+    if (pb < pa) { m = pb + 1; done = true; }
+    else { m = pa; if (pa < 32) done = true; }
+    // my group adds tiles t+gi, t+gi+ng, ... (< t+m), 8 loads in flight
+    for (int u0 = gi; u0 < m; u0 += ng * 8) {
+      float4 x[8][V];
 #pragma unroll
-    for (int u = 0; u < kAhead; ++u) {
-      fl[u] = (t + u < F.nst) ? F.st_flag[t + u] : 0;
+      for (int j = 0; j < 8; ++j) {
+        const int u = u0 + j * ng;
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-        x[u][v] = (t + u < F.nst && act[v])
-                      ? *reinterpret_cast<const float4*>(F.st_part + ((size_t)(t + u) * 2 + 0) * dim + col[v])
-                      : f4_zero();
-    }
-#pragma unroll
-    for (int u = 0; u < kAhead; ++u) {
-      if (!done) {
-        if (!(fl[u] & kFirstOpen)) {
-          done = true;
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; ++v) acc[v] = f4_add_rn(acc[v], x[u][v]);
-          if (!(fl[u] & kBoth)) done = true;
-        }
+        for (int v = 0; v < V; ++v)
+          x[j][v] = (u < m && act[v])
+                        ? *reinterpret_cast<const float4*>(F.st_part + ((size_t)(t + u) * 2 + 0) * dim + col[v])
+                        : f4_zero();
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (u0 + j * ng < m)
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = f4_add_rn(acc[v], x[j][v]);
     }
-    t += kAhead;
+    t += 32;
   }
-  if (!apply_row<V, OPT>(P, F, key, acc, col, act)) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
+  // combine the group sums in a fixed order: lanes of group gi add group gi+off
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    for (int off = ng >> 1; off >= 1; off >>= 1) {
+      float4 y;
+      y.x = __shfl_down_sync(0xffffffffu, acc[v].x, off << log2g);
+      y.y = __shfl_down_sync(0xffffffffu, acc[v].y, off << log2g);
+      y.z = __shfl_down_sync(0xffffffffu, acc[v].z, off << log2g);
+      y.w = __shfl_down_sync(0xffffffffu, acc[v].w, off << log2g);
+      if (gi < off) acc[v] = f4_add_rn(acc[v], y);
+    }
+  }
+  if (gi == 0)
+    if (!apply_row<V, OPT>(P, F, key, acc, col, act)) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
 }
 
 // bag index of every id position, for CSR features (thread per bag).
@@ -584,7 +611,9 @@ static int launch_update(const UpdParams& P, const UpdParams& X, cudaStream_t st
   }
 }
 
-static int validate_upd(int k, const hbUpdateFeature& f, const hbOptimizer* opt) {
+enum { kPhaseSort = 1, kPhaseApply = 2 };
+
+static int validate_upd(int k, const hbUpdateFeature& f, const hbOptimizer* opt, int phases) {
   HB_REQUIRE(f.dim >= 4 && f.dim % 4 == 0 && f.dim <= 1024,
              "update: feature %d dim %d must be a multiple of 4 in [4,1024]", k, f.dim);
   HB_REQUIRE(f.nnz >= 0 && f.nnz <= INT32_MAX && f.nbags >= 0 && f.nbags <= INT32_MAX,
@@ -596,8 +625,9 @@ static int validate_upd(int k, const hbUpdateFeature& f, const hbOptimizer* opt)
   HB_REQUIRE(f.grad_stride >= f.dim && f.grad_stride % 4 == 0,
              "update: feature %d grad_stride must be a multiple of 4 and >= dim", k);
   HB_REQUIRE(f.combiner >= HB_SUM && f.combiner <= HB_SQRTN, "update: feature %d bad combiner", k);
-  if (f.nnz > 0) {
-    HB_REQUIRE(f.table && f.ids && f.grad, "update: feature %d null pointer", k);
+  if (f.nnz > 0 && (phases & kPhaseSort)) HB_REQUIRE(f.ids != nullptr, "update: feature %d null ids", k);
+  if (f.nnz > 0 && (phases & kPhaseApply)) {
+    HB_REQUIRE(f.table && f.grad, "update: feature %d null pointer", k);
     HB_REQUIRE(((uintptr_t)f.table & 15) == 0 && ((uintptr_t)f.grad & 15) == 0,
                "update: feature %d table/grad must be 16-byte aligned", k);
     if (opt->kind == HB_OPT_ADAGRAD)
@@ -612,11 +642,13 @@ static int validate_upd(int k, const hbUpdateFeature& f, const hbOptimizer* opt)
 // is shared by the features of one call (1 locally, W on a row-interleaved shard).
 int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* opt, void* ws,
                       size_t ws_bytes, int32_t* d_status, cudaStream_t stream,
-                      const WaitSpec* wait, const int32_t* const* n_dev) {
+                      const WaitSpec* wait, const int32_t* const* n_dev, int phases) {
+  static const hbOptimizer kNoOpt = {HB_OPT_SGD, 0.f, 0.f, 0.f, 0.f, 1};
+  if (!(phases & kPhaseApply) && opt == nullptr) opt = &kNoOpt;
   HB_REQUIRE(n >= 1 && feats && opt, "update: bad arguments");
   HB_REQUIRE(opt->kind >= HB_OPT_SGD && opt->kind <= HB_OPT_LAZY_ADAM, "update: bad optimizer kind %d", opt->kind);
   for (int k = 0; k < n; ++k) {
-    int rc = validate_upd(k, feats[k], opt);
+    int rc = validate_upd(k, feats[k], opt, phases);
     if (rc != HB_OK) return rc;
     HB_REQUIRE(feats[k].id_div == feats[0].id_div, "update: all features of a call must share id_div");
   }
@@ -649,7 +681,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
     int32_t* counts = reinterpret_cast<int32_t*>(base + o);  // chunk-shared radix counters
 
     // 1. bag map for CSR features
-    {
+    if (phases & kPhaseSort) {
       BagMapParams B;
       B.status = d_status;
       B.nfeats = 0;
@@ -675,7 +707,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
     // 2. LSD radix sort: one memset, one histogram kernel over the ids (all digit
     //    positions), then one kernel per digit position; feature k takes part in
     //    pass p iff p < passes[k]
-    if (max_passes > 0) {
+    if (max_passes > 0 && (phases & kPhaseSort)) {
       const size_t words = bucket_scratch_words(nc, (size_t)total_tiles, kRadixBins, max_passes);
       HB_CUDA_OK(cudaMemsetAsync(counts, 0, words * sizeof(uint32_t), stream));
       BucketScratch sc = bucket_scratch_carve(reinterpret_cast<uint32_t*>(counts), nc,
@@ -735,6 +767,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
     }
 
     // 3./4. fused update + fix-up, one launch per V
+    if (!(phases & kPhaseApply)) continue;
     for (int V = 1; V <= 8; V <<= 1) {
       UpdParams U;
       U.wait = wait ? *wait : WaitSpec{nullptr, 0, 0};
@@ -771,9 +804,8 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         F.cta_begin = U.total_ctas;
         F.nst = L[k].nst;
         U.total_ctas += L[k].nst;
-        const int groups = kUpdThreads >> L[k].log2g;
         fix_begin[U.nfeats] = fix_ctas;
-        fix_ctas += (L[k].nst + groups - 1) / groups;
+        fix_ctas += (L[k].nst + (kUpdThreads / 32) - 1) / (kUpdThreads / 32);
         U.nfeats++;
       }
       if (U.nfeats == 0) continue;
@@ -823,7 +855,19 @@ int hbGroupLookupBackwardUpdate(int n, const hbUpdateFeature* feats, const hbOpt
                                 void* d_workspace, size_t workspace_bytes, int32_t* d_status,
                                 hbStream stream) {
   return hb::sparse_update_run(n, feats, opt, d_workspace, workspace_bytes, d_status,
-                               (cudaStream_t)stream, nullptr, nullptr);
+                               (cudaStream_t)stream, nullptr, nullptr, hb::kPhaseSort | hb::kPhaseApply);
+}
+
+int hbGroupSparseSort(int n, const hbUpdateFeature* feats, void* d_workspace, size_t workspace_bytes,
+                      int32_t* d_status, hbStream stream) {
+  return hb::sparse_update_run(n, feats, nullptr, d_workspace, workspace_bytes, d_status,
+                               (cudaStream_t)stream, nullptr, nullptr, hb::kPhaseSort);
+}
+
+int hbGroupSparseApply(int n, const hbUpdateFeature* feats, const hbOptimizer* opt, void* d_workspace,
+                       size_t workspace_bytes, int32_t* d_status, hbStream stream) {
+  return hb::sparse_update_run(n, feats, opt, d_workspace, workspace_bytes, d_status,
+                               (cudaStream_t)stream, nullptr, nullptr, hb::kPhaseApply);
 }
 
 }  // extern "C"

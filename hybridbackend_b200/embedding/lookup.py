@@ -92,7 +92,7 @@ class GroupLookup:
   """
 
   def __init__(self, tables, combiners=None, collective=None, max_nnz=None,
-               capacity_factor=None, sync_replicated=True):
+               capacity_factor=None, sync_replicated=True, overlap_backward_sort=True):
     self.tables = list(tables)
     self.n = len(self.tables)
     if self.n < 1:
@@ -106,6 +106,12 @@ class GroupLookup:
     self.device = _weight_of(self.tables[0]).device
     self.collective = collective
     self.sync_replicated = sync_replicated
+    # training mode: the id sort of the backward (needs only ids) is enqueued on a
+    # side stream at forward time and overlaps the forward gather
+    self.overlap_backward_sort = overlap_backward_sort
+    self._side = None
+    self._sort_done = None
+    self._upd_ws = None
     self._saved = None
     self._sharded = None
     world = collective.world_size if collective is not None else 1
@@ -123,7 +129,7 @@ class GroupLookup:
           [max_nnz[k] for k in self.sharded_idx], capacity_factor)
 
   # -- forward ---------------------------------------------------------------
-  def forward(self, ids, offsets=None, out=None, check=False):
+  def forward(self, ids, offsets=None, out=None, check=False, prepare_backward=True):
     """ids[k]: int64 [nnz_k]; offsets[k]: int64 [B+1] or None.  Returns
     out [B, sum(dim)] float32 (feature k occupies columns col_offsets[k]:+dim)."""
     offsets = list(offsets) if offsets is not None else [None] * self.n
@@ -139,6 +145,9 @@ class GroupLookup:
     st = _util.status_word(self.device)
     L = _lib.lib()
     with torch.cuda.device(self.device):
+      self._sort_done = None
+      if self.local_idx and prepare_backward and self.overlap_backward_sort and not self._needs_allgather():
+        self._presort(ids, offsets, B, st)
       if self.local_idx:
         feats = (_lib.hbLookupFeature * len(self.local_idx))()
         for j, k in enumerate(self.local_idx):
@@ -156,6 +165,53 @@ class GroupLookup:
     if check:
       _util.check_status(self.device)
     return out
+
+  def _needs_allgather(self):
+    return (self.collective is not None and self.collective.world_size > 1 and
+            self.sync_replicated and bool(self.local_idx))
+
+  def _update_feats(self, ids, offsets, B, grad=None, optimizer=None):
+    m = len(self.local_idx)
+    feats = (_lib.hbUpdateFeature * m)()
+    for j, k in enumerate(self.local_idx):
+      w = _weight_of(self.tables[k])
+      slots = self._slots(k, optimizer) if optimizer is not None else []
+      feats[j] = _lib.hbUpdateFeature(
+          w.data_ptr(), slots[0].data_ptr() if len(slots) > 0 else None,
+          slots[1].data_ptr() if len(slots) > 1 else None, w.shape[0], ids[k].data_ptr(),
+          offsets[k].data_ptr() if offsets[k] is not None else None, B, ids[k].numel(),
+          grad[:, self.col_offsets[k]:].data_ptr() if grad is not None else None,
+          grad.stride(0) if grad is not None else w.shape[1], w.shape[1],
+          _lib.COMBINER[self.combiners[k]], 1)
+    return feats
+
+  def _workspace(self, feats):
+    need = _lib.C.c_size_t(0)
+    _lib.check(_lib.lib().hbGroupSparseUpdateWorkspaceBytes(len(feats), feats, _lib.C.byref(need)),
+               'GroupLookup workspace')
+    if self._upd_ws is None or self._upd_ws.numel() < need.value:
+      self._upd_ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=self.device)
+    return self._upd_ws
+
+  def _presort(self, ids, offsets, B, st):
+    """Enqueue the backward's id sort on the side stream (hbGroupSparseSort)."""
+    if self._side is None:
+      self._side = torch.cuda.Stream(device=self.device)
+    main = torch.cuda.current_stream()
+    feats = self._update_feats(ids, offsets, B)
+    ws = self._workspace(feats)
+    ready = torch.cuda.Event()
+    ready.record(main)
+    self._side.wait_event(ready)
+    for k in self.local_idx:
+      ids[k].record_stream(self._side)
+      if offsets[k] is not None:
+        offsets[k].record_stream(self._side)
+    _lib.check(_lib.lib().hbGroupSparseSort(
+        len(feats), feats, _lib.C.c_void_p(ws.data_ptr()), _lib.C.c_size_t(ws.numel()),
+        _lib.C.c_void_p(st.data_ptr()), _lib.C.c_void_p(self._side.cuda_stream)), 'GroupLookup presort')
+    self._sort_done = torch.cuda.Event()
+    self._sort_done.record(self._side)
 
   def forward_host(self, h_ids, d_stage, out, h_out, check=False):
     """Host-buffer forward (one id per bag): h_ids pinned int64 [n, B] is copied
@@ -177,6 +233,7 @@ class GroupLookup:
     L = _lib.lib()
     ids = [d_stage[k] for k in range(self.n)]
     with torch.cuda.device(self.device):
+      self._sort_done = None
       if self._sharded is None:
         feats = (_lib.hbLookupFeature * self.n)()
         for k in range(self.n):
@@ -234,14 +291,19 @@ class GroupLookup:
               ids_k.data_ptr(), off_k.data_ptr() if off_k is not None else None,
               nb, ids_k.numel(), g_k.data_ptr(), g_stride,
               w.shape[1], _lib.COMBINER[self.combiners[k]], 1)
-        need = _lib.C.c_size_t(0)
-        _lib.check(L.hbGroupSparseUpdateWorkspaceBytes(m, feats, _lib.C.byref(need)),
-                   'GroupLookup.backward_update')
-        ws = _util.workspace(need.value, self.device, 'update')
-        _lib.check(L.hbGroupLookupBackwardUpdate(
-            m, feats, _lib.C.byref(desc), _lib.C.c_void_p(ws.data_ptr()),
-            _lib.C.c_size_t(ws.numel()), _lib.C.c_void_p(st.data_ptr()), _util.stream_ptr()),
-                   'GroupLookup.backward_update')
+        ws = self._workspace(feats)
+        if self._sort_done is not None and not sync:
+          torch.cuda.current_stream().wait_event(self._sort_done)
+          self._sort_done = None
+          _lib.check(L.hbGroupSparseApply(
+              m, feats, _lib.C.byref(desc), _lib.C.c_void_p(ws.data_ptr()),
+              _lib.C.c_size_t(ws.numel()), _lib.C.c_void_p(st.data_ptr()), _util.stream_ptr()),
+                     'GroupLookup.backward_update')
+        else:
+          _lib.check(L.hbGroupLookupBackwardUpdate(
+              m, feats, _lib.C.byref(desc), _lib.C.c_void_p(ws.data_ptr()),
+              _lib.C.c_size_t(ws.numel()), _lib.C.c_void_p(st.data_ptr()), _util.stream_ptr()),
+                     'GroupLookup.backward_update')
       if self._sharded is not None:
         self._sharded.backward_update(grad, [self.col_offsets[k] for k in self.sharded_idx],
                                       optimizer, desc, st)

@@ -41,7 +41,7 @@ enum { HB_SUM = 0, HB_MEAN = 1, HB_SQRTN = 2 };
 enum { HB_OPT_SGD = 0, HB_OPT_ADAGRAD = 1, HB_OPT_LAZY_ADAM = 2 };
 /* bits of the sticky device status word */
 enum { HB_STATUS_ID_OUT_OF_RANGE = 1, HB_STATUS_WINDOW_OVERFLOW = 2,
-       HB_STATUS_BAD_OFFSETS = 4 };
+       HB_STATUS_BAD_OFFSETS = 4, HB_STATUS_PEER_TIMEOUT = 8 };
 
 /* kernel ids for the launch counter / event profiler */
 enum { HB_K_PART_HIST = 1, HB_K_PART_PASS = 2, HB_K_RESERVED3 = 3,
@@ -164,6 +164,16 @@ int hbGroupLookupBackwardUpdate(int n, const hbUpdateFeature* feats,
                                 const hbOptimizer* opt, void* d_workspace,
                                 size_t workspace_bytes, int32_t* d_status,
                                 hbStream stream);
+/* The same in two halves, so the id sort (which needs only ids / offsets) can be
+ * enqueued on a side stream while the forward gather runs, and only the fused
+ * duplicate-sum + optimizer apply stays on the backward's critical path.  Both
+ * calls take the same feats / workspace; table, slots and grad may be NULL for
+ * hbGroupSparseSort.  hbGroupLookupBackwardUpdate == Sort followed by Apply. */
+int hbGroupSparseSort(int n, const hbUpdateFeature* feats, void* d_workspace,
+                      size_t workspace_bytes, int32_t* d_status, hbStream stream);
+int hbGroupSparseApply(int n, const hbUpdateFeature* feats, const hbOptimizer* opt,
+                       void* d_workspace, size_t workspace_bytes, int32_t* d_status,
+                       hbStream stream);
 
 /* ---------------------------------------------------------------------------
  * fp32 <-> fp16 wire casts.  Replaces functor::Cast / CastN

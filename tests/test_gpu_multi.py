@@ -212,10 +212,10 @@ def _sharded_lookup(rank, world, hb, o):
       o.sparse_apply_adagrad(ref_tables[j], ref_acc[j], np.concatenate(rows), np.concatenate(rgs), 0.05)
     for j in sh:
       got = tables[j].weight.cpu().numpy()
-      soft.allclose(got, ref_tables[j][rank::world], f'step {step} table {j}', rtol=2e-5, atol=1e-6)
+      soft.allclose(got, ref_tables[j][rank::world], f'step {step} table {j}', rtol=2e-4, atol=1e-6)
     # small (replicated) table: gradients of all ranks all-gathered, replicas identical
     got = tables[2].weight.cpu().numpy()
-    soft.allclose(got, ref_tables[2], f'step {step} replicated table', rtol=2e-5, atol=1e-6)
+    soft.allclose(got, ref_tables[2], f'step {step} replicated table', rtol=2e-4, atol=1e-6)
   torch.cuda.synchronize()
   dist.barrier()
   try:
