@@ -340,9 +340,14 @@ def run_ours(args):
   value = B * F * world * K / (ms * 1e-3)
 
   # ---- per-kernel CUDA-event pass (same K steps) for the roofline ----------------
+  # (the backward's id sort normally overlaps the forward on a side stream; for
+  # clean per-kernel durations this pass runs everything on one stream)
+  gl.overlap_backward_sort = False
+  step(0)
   L.hbProfileReset(); L.hbProfileEnable(1)
   timed(K)
   L.hbProfileEnable(0)
+  gl.overlap_backward_sort = True
   kern = {}
   import ctypes as C
   for kid in range(1, 24):
@@ -440,7 +445,7 @@ def run_ours(args):
         'gpu_launches': int(launches), 'roofline': roofline, 'roofline_all': roofs,
         'kernels': kern, 'cpu_baseline': cpu,
         'roofline_note': 'per-kernel CUDA events recorded by the library on the launching stream in '
-                         'a second pass of the same K steps (hbProfileEnable)',
+                         'a second pass of the same K steps (hbProfileEnable), single stream (no fwd/sort overlap)',
         'hbm_roofline_rows_per_s_per_gpu': peak * 1e9 / (8 + 8 * dim) if args.mode == 'fwd' else
                                            peak * 1e9 / ((8 + 8 * dim) + (8 + 20 * dim)),
     }

@@ -194,7 +194,10 @@ def _sharded_lookup(rank, world, hb, o):
       ids, off = mine[j]
       offs = off if off is not None else np.arange(len(ids) + 1, dtype=np.int64)
       exp = o.embedding_lookup_sparse(ref_tables[j], ids, offs, comb[j])
-      soft.allclose(out[:, j * D:(j + 1) * D], exp, f'step {step} feature {j}', rtol=1e-5, atol=1e-7)
+      # from the second step on the tables carry the (summation-order) differences of
+      # the previous update, so the forward is compared with an absolute tolerance
+      soft.allclose(out[:, j * D:(j + 1) * D], exp, f'step {step} feature {j}', rtol=1e-5,
+                    atol=1e-7 if step == 0 else 2e-5)
     gl.backward_update(torch.from_numpy(grads[rank]).to(dev), opt)
     # oracle: sharded tables get the SUM over ranks of the per-rank gradients
     # (training/gradient.py:216-217), applied once per step and unique row
