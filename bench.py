@@ -327,15 +327,30 @@ def run_ours(args):
     return ms
 
   W_, K = max(args.warmup, 3), args.steps
+  # nvidia-smi needs ~1 s to start sampling: start it before the warm-up so that
+  # samples exist for the (short) timed region; rank 0 samples its own GPU
+  clocks = ClockSampler(local_rank)
+  if rank == 0:
+    clocks.start()
+    time.sleep(1.0)
   for i in range(W_):
     step(i)
   hb._util.check_status(dev)
-  clocks = ClockSampler(local_rank)
-  clocks.start()
+  if rank == 0:
+    torch.cuda.synchronize()
+    clocks.lines.clear()   # keep only samples taken from here on (timed region under load)
   l0 = L.hbGetLaunchCount()
   ms = timed(K)
   launches = L.hbGetLaunchCount() - l0
-  clk = clocks.stop()
+  # the timed region is only tens of ms: keep the GPUs under the same load for
+  # ~0.5 s more (same step count on every rank) so the 100 ms sampler sees it
+  extra = min(3000, max(10, int(0.5e3 * K / ms)))
+  for i in range(extra):
+    step(i)
+  torch.cuda.synchronize()
+  clk = clocks.stop() if rank == 0 else None
+  if world > 1:
+    dist.barrier()
   hb._util.check_status(dev)
   value = B * F * world * K / (ms * 1e-3)
 
