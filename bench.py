@@ -154,12 +154,18 @@ def cpu_arm(args, sizes, dim, steps, warmup, rank0_only_note=''):
       if accs is not None:
         accs[k][u] = 0.1
 
-  # Work decomposition that uses every host core: the forward splits each feature
-  # into bag chunks (independent); the backward of a big table is split by
-  # id % parts (disjoint row sets, so the per-part dedup + Adagrad apply are
-  # independent and together equal the unsplit update).
+  # Two work decompositions; the faster one on this box is the one reported.
+  #  "feature":  one task per feature doing forward then backward (26 threads)
+  #  "split":    forward split into feature x bag-chunk tasks, backward of a big
+  #              table split by id % parts (disjoint row sets: the per-part dedup +
+  #              Adagrad applies are independent and equal the unsplit update)
   fwd_chunks = max(1, min(8, cores // F))
   bounds = np.linspace(0, B, fwd_chunks + 1).astype(np.int64)
+
+  def one_feature(k, ids):
+    o.embedding_lookup_sparse(tables[k], ids, offsets, 'mean', out=out[:, k * dim:(k + 1) * dim])
+    if accs is not None:
+      o.sparse_apply_adagrad(tables[k], accs[k], ids, np.ascontiguousarray(grad[:, k * dim:(k + 1) * dim]), 0.01)
 
   def fwd_task(k, c, ids):
     s, e = int(bounds[c]), int(bounds[c + 1])
@@ -178,26 +184,35 @@ def cpu_arm(args, sizes, dim, steps, warmup, rank0_only_note=''):
     # mean combiner with one id per bag: row gradient == bag gradient
     o.sparse_apply_adagrad(tables[k], accs[k], sel_ids, np.ascontiguousarray(g), 0.01)
 
-  workers = cores
-  ntasks = F * fwd_chunks
-  with ThreadPoolExecutor(workers) as ex:
-    def step(i):
+  with ThreadPoolExecutor(cores) as ex:
+    def step_feature(i):
       b = batches[i % nb]
-      futs = [ex.submit(fwd_task, k, c, b[k]) for k in range(F) for c in range(fwd_chunks)]
-      for f in futs:
+      list(ex.map(lambda k: one_feature(k, b[k]), range(F)))
+
+    def step_split(i):
+      b = batches[i % nb]
+      for f in [ex.submit(fwd_task, k, c, b[k]) for k in range(F) for c in range(fwd_chunks)]:
         f.result()
       if accs is not None:
-        futs = [ex.submit(bwd_task, k, p, parts_of(k), b[k]) for k in range(F)
-                for p in range(parts_of(k))]
-        for f in futs:
+        for f in [ex.submit(bwd_task, k, p, parts_of(k), b[k]) for k in range(F)
+                  for p in range(parts_of(k))]:
           f.result()
+
+    trial = {}
+    for name, fn in (('feature', step_feature), ('split', step_split)):
+      fn(0)
+      t0 = time.perf_counter()
+      fn(1)
+      trial[name] = time.perf_counter() - t0
+    mode = min(trial, key=trial.get)
+    step = step_feature if mode == 'feature' else step_split
+    workers = min(cores, F if mode == 'feature' else F * fwd_chunks)
     for i in range(warmup):
       step(i)
     t0 = time.perf_counter()
     for i in range(steps):
       step(i)
     dt = time.perf_counter() - t0
-  workers = min(cores, ntasks)
   value = B * F * steps / dt
   info = {'value': value, 'unit': 'pooled-embedding-rows/s', 'cores': workers,
           'host_cores': cores,
@@ -205,7 +220,7 @@ def cpu_arm(args, sizes, dim, steps, warmup, rank0_only_note=''):
           'sample': (f'{steps} steps x (26 feats x {B} ids) of the same workload, '
                      f'{"fwd+bwd+Adagrad" if args.mode == "train" else "fwd"}, tables '
                      f'{"full size" if scale == 1.0 else f"scaled x{scale:.2f} to fit host RAM"}, '
-                     f'{workers} threads (forward: feature x bag-chunk tasks, backward: feature x id%parts tasks); oracle/hb_oracle.c port of the '
+                     f'{workers} threads (decomposition "{mode}", the faster of feature / split on this box: {trial}); oracle/hb_oracle.c port of the '
                      'TF-1.15 CPU semantics (the tf115 wheel cannot run here)' + rank0_only_note),
           'ms_per_step': dt / steps * 1e3}
   return value, info
