@@ -164,43 +164,6 @@ __device__ __forceinline__ bool apply_row(const UpdParams& P, const UpdFeat& F, 
   return apply_rows<V, 1, OPT>(P, F, 1u, k1, g1, col, act);
 }
 
-// What a lane holds of its warp's 32-entry tile (prefetched one super-tile ahead).
-struct WarpTileIn {
-  uint32_t key, edge_key;
-  int32_t bag;
-  float scale;
-  int wcnt, n, edge_has, valid;
-};
-
-__device__ __forceinline__ void load_warp_tile(const UpdParams& P, int cta, WarpTileIn& t) {
-  const UpdFeat& F = P.f[find_upd_feat(P, cta)];
-  const int st = cta - F.cta_begin;
-  int n = F.n;
-  if (F.n_dev != nullptr) { const int d = *F.n_dev; n = d < 0 ? 0 : (d < n ? d : n); }
-  const unsigned lane = lane_id();
-  const int warp = threadIdx.x >> 5;
-  const int64_t w0 = ((int64_t)st * (kUpdThreads / 32) + warp) * 32;  // first entry of the warp
-  const int wcnt = (int)max((int64_t)0, min((int64_t)32, (int64_t)n - w0));
-  t.n = n;
-  t.wcnt = wcnt;
-  t.key = 0xFFFFFFFFu;
-  t.bag = 0;
-  if ((int)lane < wcnt) { t.key = F.keys[w0 + lane]; t.bag = F.bags[w0 + lane]; }
-  // neighbours of the warp tile
-  t.edge_key = 0;
-  t.edge_has = 0;
-  if (lane == 0 && wcnt > 0 && w0 > 0) { t.edge_key = F.keys[w0 - 1]; t.edge_has = 1; }
-  if (lane == 31 && wcnt == 32 && w0 + 32 < n) { t.edge_key = F.keys[w0 + 32]; t.edge_has = 1; }
-  t.scale = 1.0f;
-  if (F.combiner != HB_SUM && F.offsets != nullptr && (int)lane < wcnt) {
-    const int64_t c = F.offsets[t.bag + 1] - F.offsets[t.bag];
-    t.scale = (F.combiner == HB_MEAN) ? (float)c : __fsqrt_rn((float)c);
-  }
-  t.valid = 1;
-}
-
-// Persistent CTAs walk the super-tiles (256 sorted entries each); the keys/bags of
-// the next super-tile are fetched while the current one is being combined.
 // A warp owns 32 consecutive sorted entries (lane e holds key/bag of entry e: one
 // coalesced load each); the run structure of the warp tile is a pair of ballot
 // masks.  Each of the 32/G groups walks its G consecutive entries in sub-batches
@@ -212,18 +175,17 @@ __global__ void __launch_bounds__(kUpdThreads, (V == 1 ? 3 : 1))
 sparse_update_kernel(const __grid_constant__ UpdParams P) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   wait_spec(P.wait, P.status);
-  WarpTileIn pf;
-  pf.valid = 0;
-  for (int cta = blockIdx.x; cta < P.total_ctas; cta += gridDim.x) {
-  const int fi = find_upd_feat(P, cta);
+  const int fi = find_upd_feat(P, blockIdx.x);
   const UpdFeat& F = P.f[fi];
-  const int st = cta - F.cta_begin;
+  const int st = blockIdx.x - F.cta_begin;
   const int log2g = F.log2g;
   const int G = 1 << log2g;
   const int groups = kUpdThreads >> log2g;
   const int g = threadIdx.x >> log2g;
   const int l = threadIdx.x & (G - 1);
   const int dim = F.dim;
+  int n = F.n;
+  if (F.n_dev != nullptr) { const int d = *F.n_dev; n = d < 0 ? 0 : (d < n ? d : n); }
   // smem carve-up
   float4* s_part = reinterpret_cast<float4*>(s_raw);                  // [groups][2][V][G]
   uint32_t* s_key = reinterpret_cast<uint32_t*>(s_part + (size_t)groups * 2 * V * G);  // [groups][2]
@@ -239,18 +201,25 @@ sparse_update_kernel(const __grid_constant__ UpdParams P) {
   bool oob = false;
   int flag = 0;
 
-  // ---- warp tile: 32 entries, lane e <-> entry e (prefetched by the previous
-  // iteration, loaded here only for a CTA's first super-tile) ----------------------
+  // ---- warp tile: 32 entries, lane e <-> entry e -------------------------------
   const unsigned lane = lane_id();
-  if (!pf.valid) load_warp_tile(P, cta, pf);
-  const int wcnt = pf.wcnt;
-  const uint32_t my_key = pf.key;
-  const int32_t my_bag = pf.bag;
-  const uint32_t edge_key = pf.edge_key;
-  const bool edge_has = pf.edge_has != 0;
-  const float my_scale = pf.scale;
+  const int warp = threadIdx.x >> 5;
+  const int64_t w0 = ((int64_t)st * (kUpdThreads / 32) + warp) * 32;  // first entry of the warp
+  const int wcnt = (int)max((int64_t)0, min((int64_t)32, (int64_t)n - w0));
+  uint32_t my_key = 0xFFFFFFFFu;
+  int32_t my_bag = 0;
+  if ((int)lane < wcnt) { my_key = F.keys[w0 + lane]; my_bag = F.bags[w0 + lane]; }
+  // neighbours of the warp tile
+  uint32_t edge_key = 0;
+  bool edge_has = false;
+  if (lane == 0 && wcnt > 0 && w0 > 0) { edge_key = F.keys[w0 - 1]; edge_has = true; }
+  if (lane == 31 && wcnt == 32 && w0 + 32 < n) { edge_key = F.keys[w0 + 32]; edge_has = true; }
+  float my_scale = 1.0f;
   const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
-  pf.valid = 0;
+  if (scaled && (int)lane < wcnt) {
+    const int64_t c = F.offsets[my_bag + 1] - F.offsets[my_bag];
+    my_scale = (F.combiner == HB_MEAN) ? (float)c : __fsqrt_rn((float)c);
+  }
   // same_prev bit e: entry e has the same key as entry e-1 (globally)
   const uint32_t up_key = __shfl_up_sync(0xffffffffu, my_key, 1);
   bool sp = false;
@@ -386,8 +355,6 @@ sparse_update_kernel(const __grid_constant__ UpdParams P) {
       for (int v = 0; v < V; ++v) carry[v] = gv[SB - 1][v];
     }
   }
-  // fetch the next super-tile's keys/bags now: they arrive during the combine
-  if (cta + (int)gridDim.x < P.total_ctas) load_warp_tile(P, cta + gridDim.x, pf);
   __shared__ int s_stflag;
   if (threadIdx.x == 0) s_stflag = 0;
   if (l == 0) s_flag[g] = flag;
@@ -450,7 +417,6 @@ sparse_update_kernel(const __grid_constant__ UpdParams P) {
   if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
   __syncthreads();
   if (threadIdx.x == 0) F.st_flag[st] = s_stflag;
-  }  // persistent loop over super-tiles
 }
 
 // Finish rows that span super-tiles (hot keys): one WARP per super-tile that
@@ -624,13 +590,8 @@ static int launch_update_opt(const UpdParams& P, const UpdParams& X, cudaStream_
     HB_CUDA_OK(cudaFuncSetAttribute(sparse_update_kernel<V, OPT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (P.total_ctas > 0) {
-    int per_sm = 0;
-    HB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sparse_update_kernel<V, OPT>,
-                                                             kUpdThreads, smem));
-    const int maxg = device_sm_count() * (per_sm > 0 ? per_sm : 1);
-    const int grid = P.total_ctas < maxg ? P.total_ctas : maxg;
     KernelScope ks(HB_K_SPARSE_UPDATE, stream);
-    sparse_update_kernel<V, OPT><<<grid, kUpdThreads, smem, stream>>>(P);
+    sparse_update_kernel<V, OPT><<<P.total_ctas, kUpdThreads, smem, stream>>>(P);
   }
   HB_CUDA_OK(cudaGetLastError());
   if (X.total_ctas > 0) {
