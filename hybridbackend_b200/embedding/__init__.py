@@ -7,3 +7,7 @@ from hybridbackend_b200.embedding.lookup import embedding_lookup
 from hybridbackend_b200.embedding.lookup import embedding_lookup_sparse
 from hybridbackend_b200.embedding.lookup import GroupLookup
 from hybridbackend_b200.embedding.lookup import segment_ids_to_offsets
+from hybridbackend_b200.embedding.cache import lookup
+from hybridbackend_b200.embedding.checkpoint import merge_shards
+from hybridbackend_b200.embedding.checkpoint import logical_rows_of_merged
+from hybridbackend_b200.embedding.checkpoint import split_merged

@@ -62,3 +62,21 @@ def test_cache_lookup(hb, oracle, slabs, nkeys):
   idx, pay = idx.cpu().numpy(), pay.cpu().numpy()
   assert set(zip(idx[:nh].tolist(), pay[:nh].tolist())) == set(zip(hi.tolist(), hc.tolist()))
   assert set(zip(idx[n - nm:].tolist(), pay[n - nm:].tolist())) == set(zip(mi.tolist(), mk.tolist()))
+
+
+def test_lookup_python_surface(hb, oracle):
+  """hb.embedding.lookup mirrors the HbLookup op outputs."""
+  rng = np.random.RandomState(5)
+  slabs = 16
+  present = rng.choice(10**5, size=300, replace=False).astype(np.int64)
+  cache = _build_cache(oracle, slabs, present)
+  q = np.concatenate([rng.choice(present, 200), rng.randint(10**5, 2 * 10**5, 100)]).astype(np.int64)
+  hk, hc, mk_idx, mk = hb.embedding.lookup(torch.from_numpy(cache).cuda(), torch.from_numpy(q).cuda())
+  hi, hcache, mi, mkeys = oracle.cache_lookup(cache, q)
+  assert set(zip(hk.tolist(), hc.tolist())) == set(zip(hi.tolist(), hcache.tolist()))
+  assert set(zip(mk_idx.tolist(), mk.tolist())) == set(zip(mi.tolist(), mkeys.tolist()))
+  assert np.array_equal(cache[hc.cpu().numpy()], q[hk.cpu().numpy()])
+  e = hb.embedding.lookup(torch.from_numpy(cache).cuda(), torch.empty(0, dtype=torch.int64, device='cuda'))
+  assert all(t.numel() == 0 for t in e)
+  with pytest.raises(ValueError, match='1D'):
+    hb.embedding.lookup(torch.zeros(2, 32, dtype=torch.int64, device='cuda'), torch.zeros(1, dtype=torch.int64, device='cuda'))

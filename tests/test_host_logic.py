@@ -116,3 +116,25 @@ def test_sharded_recipe_over_gloo_world2(oracle):
   sizes = np.stack([oracle.partition_by_modulo(i, world)[1] for i in ids])
   for rank, _, rs in res:
     assert rs == sizes[:, rank].tolist()
+
+
+def test_checkpoint_layout_roundtrip(hb):
+  """Merged checkpoint layout (variables.py:118-132): contiguous SaveSliceInfo
+  blocks of row-interleaved shards; round trip and logical permutation."""
+  from hybridbackend_b200.embedding import checkpoint, sharding
+  for n, w in ((10, 4), (1003, 8), (7, 2)):
+    table = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)   # logical order
+    parts = [table[s::w] for s in range(w)]                           # sharding.py:185-186
+    merged = checkpoint.merge_shards(parts, n)
+    back = checkpoint.split_merged(merged, w)
+    for s in range(w):
+      assert torch.equal(back[s], parts[s])
+      off = sharding.shard_offset(n, w, s)
+      # merged row off + r holds logical id r*w + s
+      for r in (0, parts[s].shape[0] - 1):
+        assert torch.equal(merged[off + r], table[r * w + s])
+    perm = checkpoint.logical_rows_of_merged(n, w)
+    assert sorted(perm.tolist()) == list(range(n))
+    logical = torch.empty_like(merged)
+    logical[perm] = merged
+    assert torch.equal(logical, table)
