@@ -234,7 +234,7 @@ bucket_hist_kernel(const __grid_constant__ BucketParams P) {
 
 // ---- pass -------------------------------------------------------------------
 template <typename Tr>
-__global__ void __launch_bounds__(kBucketThreads)
+__global__ void __launch_bounds__(kBucketThreads, 4)
 bucket_pass_kernel(const __grid_constant__ BucketParams P) {
   using In = typename Tr::In;
   using Out = typename Tr::Out;

@@ -112,7 +112,7 @@ __device__ __forceinline__ void load_rows(const LookupFeat& F, int cid, int64_t 
 // fetched while the rows of the current chunk are in flight, so every iteration
 // exposes a single memory round trip with 4 x 128-bit loads per lane outstanding.
 template <int V, bool COH>
-__global__ void __launch_bounds__(kLookupThreads)
+__global__ void __launch_bounds__(kLookupThreads, (V == 1 ? 4 : 1))
 lookup_fwd_kernel(const __grid_constant__ LookupParams P) {
   wait_spec(P.wait, P.status);
   bool oob = false;
