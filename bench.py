@@ -198,21 +198,18 @@ def cpu_arm(args, sizes, dim, steps, warmup, rank0_only_note=''):
                   for p in range(parts_of(k))]:
           f.result()
 
+    # time BOTH decompositions for the full step count and report the faster one
     trial = {}
     for name, fn in (('feature', step_feature), ('split', step_split)):
-      fn(0)
+      for i in range(max(1, warmup)):
+        fn(i)
       t0 = time.perf_counter()
-      fn(1)
-      trial[name] = time.perf_counter() - t0
+      for i in range(steps):
+        fn(i)
+      trial[name] = (time.perf_counter() - t0) / steps
     mode = min(trial, key=trial.get)
-    step = step_feature if mode == 'feature' else step_split
     workers = min(cores, F if mode == 'feature' else F * fwd_chunks)
-    for i in range(warmup):
-      step(i)
-    t0 = time.perf_counter()
-    for i in range(steps):
-      step(i)
-    dt = time.perf_counter() - t0
+    dt = trial[mode] * steps
   value = B * F * steps / dt
   info = {'value': value, 'unit': 'pooled-embedding-rows/s', 'cores': workers,
           'host_cores': cores,
@@ -220,7 +217,7 @@ def cpu_arm(args, sizes, dim, steps, warmup, rank0_only_note=''):
           'sample': (f'{steps} steps x (26 feats x {B} ids) of the same workload, '
                      f'{"fwd+bwd+Adagrad" if args.mode == "train" else "fwd"}, tables '
                      f'{"full size" if scale == 1.0 else f"scaled x{scale:.2f} to fit host RAM"}, '
-                     f'{workers} threads (decomposition "{mode}", the faster of feature / split on this box: {trial}); oracle/hb_oracle.c port of the '
+                     f'{workers} threads (decomposition "{mode}", the faster of the two decompositions, s/step: {trial}); oracle/hb_oracle.c port of the '
                      'TF-1.15 CPU semantics (the tf115 wheel cannot run here)' + rank0_only_note),
           'ms_per_step': dt / steps * 1e3}
   return value, info
