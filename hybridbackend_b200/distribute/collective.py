@@ -79,25 +79,50 @@ class Collective:
       _lib.check(_lib.lib().hbCommBarrier(self._comm, _util.stream_ptr()), 'barrier')
 
   # -- alltoall ------------------------------------------------------------------
+  def _cast_n(self, tensors, to_dtype):
+    """fp32 <-> fp16 for N tensors in one launch (hbCastN; the reference's CastN,
+    common/cast.cu.cc:84-495, used when comm_wire_dtype is float16)."""
+    outs = [torch.empty(t.shape, dtype=to_dtype, device=t.device) for t in tensors]
+    if not tensors:
+      return outs
+    with torch.cuda.device(tensors[0].device):
+      _lib.check(_lib.lib().hbCastN(
+          len(tensors), _lib.ptr_array([t.data_ptr() for t in tensors]),
+          _lib.ptr_array([o.data_ptr() for o in outs]), _lib.i64_array([t.numel() for t in tensors]),
+          _util.dtype_code(tensors[0]), _lib.DTYPE['float16' if to_dtype == torch.float16 else 'float32'],
+          _util.stream_ptr()), 'cast')
+    return outs
+
   def alltoall(self, value, sizes=None, common_shape=None, topology=Topology.ALL,
-               name=None):
+               name=None, wire_dtype=None):
     """Shuffle value partitions across devices (collective.py:271-350).
 
     sizes=None: equal split of dim 0 across ranks (HbNcclAlltoall); otherwise
     `sizes[r]` rows of `value` go to rank r and (output, output_sizes) is
-    returned, output = concat over source ranks of the segments addressed to me."""
+    returned, output = concat over source ranks of the segments addressed to me.
+    wire_dtype=torch.float16 sends float32 payloads as half on the wire (lossy; the
+    reference's `comm_wire_dtype` option, collective.py:291-296,
+    nccl_alltoallv.cc:57-88)."""
     del name
     if topology != Topology.ALL:
       raise NotImplementedError('only Topology.ALL is built (single NVSwitch domain); '
                                 'INTRA/INTER_NODE belong to the multi-node path')
     single = isinstance(value, torch.Tensor)
     values = [value] if single else list(value)
+    half_wire = (wire_dtype == torch.float16 and self.world_size > 1 and
+                 all(v.dtype == torch.float32 for v in values))
+    if half_wire:
+      values = self._cast_n([_util.require_cuda(v, 'alltoall: value') for v in values], torch.float16)
     if sizes is None:
       outs = self._alltoall_equal(values)
+      if half_wire:
+        outs = self._cast_n(outs, torch.float32)
       return outs[0] if single else outs
     szs = [sizes] if single else list(sizes)
     shapes = None if common_shape is None else ([common_shape] if single else list(common_shape))
     outs, osz = self._alltoallv_n(values, szs, shapes)
+    if half_wire:
+      outs = self._cast_n(outs, torch.float32)
     if single:
       return outs[0], osz[0]
     return outs, osz

@@ -94,6 +94,15 @@ def _alltoallv_golden(rank, world, hb, o):
   outs, oszs = coll.alltoall(vals, sizes=szs)
   for k in range(2):
     assert outs[k].tolist() == exp[rank][k][0] and oszs[k].tolist() == exp[rank][k][1]
+  # alltoall_test.py:245-252 / :271-286: float payload over a float16 wire
+  out, osz = coll.alltoall(torch.tensor([float(v) for v in ids[rank]], device='cuda'),
+                           sizes=torch.tensor(sizes[rank], dtype=torch.int32, device='cuda'),
+                           wire_dtype=torch.float16)
+  assert out.dtype == torch.float32 and out.tolist() == [float(v) for v in exp_ids[rank]]
+  assert osz.tolist() == exp_sz[rank]
+  outs, oszs = coll.alltoall(vals, sizes=szs, wire_dtype=torch.float16)
+  for k in range(2):
+    assert outs[k].tolist() == exp[rank][k][0] and oszs[k].tolist() == exp[rank][k][1]
   # equal-split alltoall (alltoall_test.py:200-205): expected = transpose of inputs
   full = [torch.arange(6, dtype=torch.float32).reshape(2, 3) + 10 * d for d in range(world)]
   got = coll.alltoall(full[rank].cuda())
