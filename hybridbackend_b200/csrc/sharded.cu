@@ -540,7 +540,7 @@ int hbShardedPlanCreate(hbComm* comm, int n, const int64_t* max_nnz, const int32
                         double capacity_factor, hbShardedPlan** plan) {
   using namespace hb;
   HB_REQUIRE(comm && comm->connected, "hbShardedPlanCreate: communicator not connected");
-  HB_REQUIRE(n >= 1 && n <= kMaxA2aTensors, "hbShardedPlanCreate: n=%d not in [1,%d]", n, kMaxA2aTensors);
+  HB_REQUIRE(n >= 1 && n <= kShMaxFeats, "hbShardedPlanCreate: n=%d not in [1,%d] sharded features per plan", n, kShMaxFeats);
   HB_REQUIRE(max_nnz && dims && plan, "hbShardedPlanCreate: null argument");
   HB_REQUIRE(comm->reserved_bytes == 0, "hbShardedPlanCreate: this communicator already hosts a plan");
   if (capacity_factor < 1.0) capacity_factor = 1.0;
