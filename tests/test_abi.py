@@ -85,3 +85,44 @@ def test_product_does_not_import_oracle():
         txt = open(os.path.join(dirpath, fn)).read()
         assert 'hb_oracle' not in txt.replace('oracle/hb_oracle.c:', ''), fn
         assert 'import oracle' not in txt and 'from oracle' not in txt, fn
+
+
+def test_struct_layouts_match_header(hb, tmp_path):
+  """The ctypes mirrors in hybridbackend_b200/_lib.py must have exactly the layout a C
+  compiler gives the structs of include/hb_b200.h (sizeof + every field offset)."""
+  import subprocess
+  lib = hb._lib
+  structs = {'hbLookupFeature': lib.hbLookupFeature, 'hbUpdateFeature': lib.hbUpdateFeature,
+             'hbOptimizer': lib.hbOptimizer, 'hbShardedFeature': lib.hbShardedFeature}
+  lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "hb_b200.h"', 'int main(void) {']
+  for name, st in structs.items():
+    lines.append(f'  printf("{name} sizeof %zu\\n", sizeof({name}));')
+    for fname, _ in st._fields_:
+      lines.append(f'  printf("{name} {fname} %zu\\n", offsetof({name}, {fname}));')
+  lines += ['  return 0;', '}']
+  src = tmp_path / 'layout.c'
+  src.write_text('\n'.join(lines))
+  exe = tmp_path / 'layout'
+  subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+  out = subprocess.check_output([str(exe)], text=True)
+  for line in out.strip().splitlines():
+    name, field, val = line.split()
+    st = structs[name]
+    if field == 'sizeof':
+      assert C.sizeof(st) == int(val), f'{name}: ctypes {C.sizeof(st)} != C {val}'
+    else:
+      assert getattr(st, field).offset == int(val), f'{name}.{field}'
+
+
+def test_header_is_plain_c(tmp_path):
+  """The boundary header must compile as C99 with no CUDA / C++ / torch includes."""
+  import subprocess
+  src = tmp_path / 'h.c'
+  src.write_text('#include "hb_b200.h"\nint main(void) { return HB_OK; }\n')
+  subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'),
+                         str(src), '-o', str(tmp_path / 'h')])
+  txt = open(os.path.join(ROOT, 'include', 'hb_b200.h')).read()
+  code = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)   # comments cite reference paths
+  includes = re.findall(r'#include\s*[<"]([^>"]+)[>"]', code)
+  assert sorted(includes) == ['stddef.h', 'stdint.h'], includes
+  assert 'torch' not in code and 'Tensor' not in code
