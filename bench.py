@@ -17,7 +17,6 @@ through the C-ABI host entry (hbGroupLookupForwardHost).
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
