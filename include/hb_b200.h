@@ -275,7 +275,12 @@ typedef struct hbShardedFeature {
 typedef struct hbShardedPlan hbShardedPlan;
 /* max_nnz[k]: static upper bound of nnz for feature k on ANY rank;
  * capacity_factor >= 1: owner-side receive capacity per feature =
- * ceil(capacity_factor * max_nnz[k]) ids (W*max_nnz is always safe). */
+ * ceil(capacity_factor * max_nnz[k]) ids (W*max_nnz is always safe; receive counts
+ * stay on the device, so capacity costs memory, not work).  Overflow raises
+ * HB_STATUS_WINDOW_OVERFLOW.  Limits: n <= 64 features per plan, all dims <= 128
+ * (or all in the same 128-wide class); one plan per communicator.  Every rank
+ * must issue the same Forward / BackwardUpdate sequence; a peer that never
+ * arrives raises HB_STATUS_PEER_TIMEOUT after 20 s instead of hanging. */
 int hbShardedPlanCreate(hbComm* comm, int n, const int64_t* max_nnz,
                         const int32_t* dims, double capacity_factor,
                         hbShardedPlan** plan);
