@@ -153,7 +153,8 @@ def cpu_arm(args, sizes, dim, steps, warmup, rank0_only_note=''):
       if accs is not None:
         accs[k][u] = 0.1
 
-  # Two work decompositions; the faster one on this box is the one reported.
+  # Three work decompositions; the fastest one on this box is the one reported.
+  #  "pthreads": C work queue over (feature, bag-chunk) and (feature, row-part) tasks
   #  "feature":  one task per feature doing forward then backward (26 threads)
   #  "split":    forward split into feature x bag-chunk tasks, backward of a big
   #              table split by id % parts (disjoint row sets: the per-part dedup +
@@ -197,9 +198,16 @@ def cpu_arm(args, sizes, dim, steps, warmup, rank0_only_note=''):
                   for p in range(parts_of(k))]:
           f.result()
 
-    # time BOTH decompositions for the full step count and report the faster one
+    def step_pthreads(i):
+      # the same per-feature oracle functions driven by a C pthread work queue
+      # (oracle/hb_oracle_mt.c): no Python in the loop
+      bt = batches[i % nb]
+      o.mt_step(tables, accs, [bt[k] for k in range(F)], grad, out, 0.01, cores,
+                fwd_chunk=8192, parts=[parts_of(k) for k in range(F)])
+
+    # time ALL decompositions for the full step count and report the fastest one
     trial = {}
-    for name, fn in (('feature', step_feature), ('split', step_split)):
+    for name, fn in (('feature', step_feature), ('split', step_split), ('pthreads', step_pthreads)):
       for i in range(max(1, warmup)):
         fn(i)
       t0 = time.perf_counter()
@@ -207,7 +215,7 @@ def cpu_arm(args, sizes, dim, steps, warmup, rank0_only_note=''):
         fn(i)
       trial[name] = (time.perf_counter() - t0) / steps
     mode = min(trial, key=trial.get)
-    workers = min(cores, F if mode == 'feature' else F * fwd_chunks)
+    workers = cores if mode == 'pthreads' else min(cores, F if mode == 'feature' else F * fwd_chunks)
     dt = trial[mode] * steps
   value = B * F * steps / dt
   info = {'value': value, 'unit': 'pooled-embedding-rows/s', 'cores': workers,
@@ -216,7 +224,7 @@ def cpu_arm(args, sizes, dim, steps, warmup, rank0_only_note=''):
           'sample': (f'{steps} steps x (26 feats x {B} ids) of the same workload, '
                      f'{"fwd+bwd+Adagrad" if args.mode == "train" else "fwd"}, tables '
                      f'{"full size" if scale == 1.0 else f"scaled x{scale:.2f} to fit host RAM"}, '
-                     f'{workers} threads (decomposition "{mode}", the faster of the two decompositions, s/step: {trial}); oracle/hb_oracle.c port of the '
+                     f'{workers} threads (decomposition "{mode}", the fastest of three thread decompositions, s/step: {trial}); oracle/hb_oracle.c port of the '
                      'TF-1.15 CPU semantics (the tf115 wheel cannot run here)' + rank0_only_note),
           'ms_per_step': dt / steps * 1e3}
   return value, info

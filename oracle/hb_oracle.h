@@ -118,6 +118,29 @@ int64_t hbo_cache_lookup(const int64_t* keys_cache, int64_t slabs,
                          int64_t* hit_cache, int32_t* miss_idx,
                          int64_t* miss_keys, int64_t* n_hit);
 
+/* ---------------------------------------------------------------------------
+ * Multi-threaded step of the same CPU semantics (pthreads), used only by
+ * bench.py's CPU legs: forward = embedding_lookup_sparse per (feature,
+ * bag-chunk) task, backward = dedup + SparseApplyAdagrad per (feature,
+ * row-residue part) task (parts own disjoint rows, so the union equals the
+ * unsplit update).  One id per bag.  Returns 0 on success.
+ * ------------------------------------------------------------------------- */
+typedef struct hbo_mt_feature {
+  float* table;
+  float* accum;       /* NULL: forward only */
+  int64_t rows;
+  int32_t dim;
+  int32_t parts;      /* backward tasks for this feature (>= 1) */
+  const int64_t* ids; /* [nbags] */
+  int64_t nbags;
+  const float* grad;  /* [nbags, grad_stride] */
+  int64_t grad_stride;
+  float* out;         /* [nbags, out_stride] */
+  int64_t out_stride;
+} hbo_mt_feature;
+
+int hbo_mt_step(int nfeat, const hbo_mt_feature* feats, int64_t fwd_chunk, float lr, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

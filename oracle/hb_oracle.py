@@ -20,8 +20,9 @@ COMBINER = {'sum': 0, 'mean': 1, 'sqrtn': 2}
 def build(force=False):
   so = os.path.join(_HERE, 'libhb_oracle.so')
   src = os.path.join(_HERE, 'hb_oracle.c')
-  if force or not os.path.exists(so) or (
-      os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+  srcs = [src, os.path.join(_HERE, 'hb_oracle_mt.c'), os.path.join(_HERE, 'hb_oracle.h')]
+  if force or not os.path.exists(so) or any(
+      os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
     subprocess.check_call(['make', '-C', _HERE, 'libhb_oracle.so'],
                           stdout=subprocess.DEVNULL)
   if os.path.isdir('/root/reference/hybridbackend'):
@@ -252,3 +253,27 @@ def cache_lookup(keys_cache, keys):
                               C.c_int64(n), _p(hi), _p(hc), _p(mi), _p(mk),
                               C.byref(nh))
   return hi[:nh.value], hc[:nh.value], mi[:nm], mk[:nm]
+
+
+class _MtFeature(C.Structure):
+  _fields_ = [('table', C.c_void_p), ('accum', C.c_void_p), ('rows', C.c_int64), ('dim', C.c_int32),
+              ('parts', C.c_int32), ('ids', C.c_void_p), ('nbags', C.c_int64), ('grad', C.c_void_p),
+              ('grad_stride', C.c_int64), ('out', C.c_void_p), ('out_stride', C.c_int64)]
+
+
+def mt_step(tables, accums, ids, grad, out, lr, nthreads, fwd_chunk=8192, parts=None):
+  """One forward(+backward) step over F one-id-per-bag features on `nthreads`
+  pthreads (hbo_mt_step).  tables/accums: lists of [rows, dim] float32 arrays
+  (accums None: forward only); ids: list of int64 [B]; grad/out: [B, F*dim]."""
+  F = len(tables)
+  dim = tables[0].shape[1]
+  feats = (_MtFeature * F)()
+  for k in range(F):
+    g = grad[:, k * dim:(k + 1) * dim]
+    oo = out[:, k * dim:(k + 1) * dim]
+    feats[k] = _MtFeature(tables[k].ctypes.data, accums[k].ctypes.data if accums is not None else None,
+                          tables[k].shape[0], dim, 1 if parts is None else int(parts[k]),
+                          ids[k].ctypes.data, ids[k].shape[0], g.ctypes.data, grad.strides[0] // 4,
+                          oo.ctypes.data, out.strides[0] // 4)
+  rc = lib().hbo_mt_step(F, feats, C.c_int64(fwd_chunk), C.c_float(lr), int(nthreads))
+  _check(rc, 'mt_step')

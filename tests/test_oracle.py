@@ -266,3 +266,27 @@ def test_cache_lookup_oracle(oracle):
   np.testing.assert_array_equal(cache[hc], [100, 159, 130])
   np.testing.assert_array_equal(mi, [1, 3])
   np.testing.assert_array_equal(mk, [5, 777])
+
+
+def test_mt_step_equals_single_thread(oracle):
+  """oracle/hb_oracle_mt.c (pthread driver of bench.py's CPU legs) == the plain oracle."""
+  rng = np.random.RandomState(0)
+  F, B, D = 5, 3000, 8
+  rows = [50000, 3, 700, 2000000, 64]
+  T = [rng.randn(r, D).astype(np.float32) for r in rows]
+  A = [np.full((r, D), 0.1, np.float32) for r in rows]
+  T2 = [t.copy() for t in T]
+  A2 = [a.copy() for a in A]
+  ids = [(rng.zipf(1.2, B) % r).astype(np.int64) for r in rows]
+  grad = rng.randn(B, F * D).astype(np.float32)
+  out = np.empty((B, F * D), np.float32)
+  out2 = np.empty_like(out)
+  oracle.mt_step(T, A, ids, grad, out, 0.01, 8, fwd_chunk=777, parts=[4, 1, 2, 8, 1])
+  off = np.arange(B + 1, dtype=np.int64)
+  for k in range(F):
+    oracle.embedding_lookup_sparse(T2[k], ids[k], off, 'mean', out=out2[:, k * D:(k + 1) * D])
+  for k in range(F):
+    oracle.sparse_apply_adagrad(T2[k], A2[k], ids[k], np.ascontiguousarray(grad[:, k * D:(k + 1) * D]), 0.01)
+  assert np.array_equal(out, out2)
+  for k in range(F):
+    assert np.array_equal(T[k], T2[k]) and np.array_equal(A[k], A2[k])
