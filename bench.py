@@ -384,7 +384,7 @@ def run_ours(args):
   gl.overlap_backward_sort = True
   kern = {}
   import ctypes as C
-  for kid in range(1, 24):
+  for kid in range(1, 32):
     tms, n = C.c_double(0), C.c_int64(0)
     L.hbProfileGet(kid, C.byref(tms), C.byref(n))
     if n.value:

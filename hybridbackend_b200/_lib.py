@@ -13,8 +13,7 @@ _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, 'csrc')
 _SO = os.path.join(_PKG, 'lib', 'libhb_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
-              '-std=c++17', '-Xcompiler', '-fPIC', '--use_fast_math=false']
-NVCC_FLAGS = [f for f in NVCC_FLAGS if f != '--use_fast_math=false']
+              '-std=c++17', '-Xcompiler', '-fPIC']
 
 
 def sources():
@@ -64,7 +63,7 @@ class hbLookupFeature(C.Structure):
   _fields_ = [('table', C.c_void_p), ('rows', C.c_int64), ('ids', C.c_void_p),
               ('offsets', C.c_void_p), ('nbags', C.c_int64), ('out', C.c_void_p),
               ('out_stride', C.c_int64), ('dim', C.c_int32), ('combiner', C.c_int32),
-              ('id_div', C.c_int64)]
+              ('id_div', C.c_int64), ('nnz', C.c_int64)]
 
 
 class hbUpdateFeature(C.Structure):
@@ -77,7 +76,8 @@ class hbUpdateFeature(C.Structure):
 
 class hbOptimizer(C.Structure):
   _fields_ = [('kind', C.c_int32), ('lr', C.c_float), ('beta1', C.c_float),
-              ('beta2', C.c_float), ('eps', C.c_float), ('step', C.c_int64)]
+              ('beta2', C.c_float), ('eps', C.c_float), ('flags', C.c_int32),
+              ('step', C.c_int64)]
 
 
 class hbShardedFeature(C.Structure):
@@ -96,6 +96,8 @@ OPT = {'sgd': 0, 'adagrad': 1, 'lazy_adam': 2}
 STATUS_ID_OUT_OF_RANGE = 1
 STATUS_WINDOW_OVERFLOW = 2
 STATUS_BAD_OFFSETS = 4
+STATUS_PEER_TIMEOUT = 8
+OPT_FLAG_FAST_MATH = 1
 TOKEN_BYTES = 128
 
 # every symbol include/hb_b200.h declares (tests check the .so exports all)
@@ -105,7 +107,8 @@ SYMBOLS = [
     'hbPartitionWorkspaceBytes', 'hbPartitionByModuloN', 'hbPartitionByDualModuloN',
     'hbGroupLookupForward', 'hbGroupSparseUpdateWorkspaceBytes',
     'hbGroupLookupBackwardUpdate', 'hbGroupSparseSort', 'hbGroupSparseApply', 'hbCastN', 'hbCacheLookup',
-    'hbCommCreate', 'hbCommConnect', 'hbCommDestroy', 'hbCommRank', 'hbCommWorldSize',
+    'hbCommCreate', 'hbCommConnect', 'hbCommCreateLocalGroup', 'hbCommSetStatusWord',
+    'hbAllreduceSumF32', 'hbCommDestroy', 'hbCommRank', 'hbCommWorldSize',
     'hbCommWindow', 'hbCommWindowBytes', 'hbCommBarrier',
     'hbAlltoallvNSizes', 'hbAlltoallvN',
     'hbShardedPlanCreate', 'hbShardedPlanDestroy', 'hbShardedPlanWindowBytes',

@@ -49,10 +49,14 @@ _status = {}
 
 
 def status_word(device):
-  w = _status.get(device)
+  """Sticky device status word of the calling thread (one rank per thread when an
+  in-process group of communicators shares a device)."""
+  import threading  # pylint: disable=import-outside-toplevel
+  key = (torch.device(device), threading.get_ident())
+  w = _status.get(key)
   if w is None:
     w = torch.zeros(1, dtype=torch.int32, device=device)
-    _status[device] = w
+    _status[key] = w
   return w
 
 
@@ -67,7 +71,7 @@ def check_status(device, clear=True):
     raise IndexError('embedding id out of range for its table')
   if v & _lib.STATUS_BAD_OFFSETS:
     raise ValueError('bag offsets are not non-decreasing / within nnz')
-  if v & 8:
+  if v & _lib.STATUS_PEER_TIMEOUT:
     raise RuntimeError('timed out waiting for a peer rank (a rank crashed or ranks issued '
                        'different collective sequences)')
   if v & _lib.STATUS_WINDOW_OVERFLOW:

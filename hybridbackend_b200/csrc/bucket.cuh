@@ -54,6 +54,7 @@ struct BucketSeg {
   uint32_t key_limit;      // radix-first: keys >= key_limit are invalid (0: off)
   int32_t hist_slot;       // histogram row of this segment: hist[(hist_slot*npass + pass)*nbins]
   int32_t passes;          // number of digit positions this segment needs
+  int32_t lbits;           // composite keys: bits of the local row (owner sits above them)
 };
 
 struct BucketParams {
@@ -120,6 +121,43 @@ struct RadixFirstTraits {  // int64 global id -> uint32 local row, first digit
     if (v < 0) return 0xFFFFFFFEu;           // invalid id: skipped, raises the status word
     const uint64_t r = (P.div_shift >= 0) ? ((uint64_t)v >> P.div_shift) : (uint64_t)(v / P.div);
     return (r >= (uint64_t)sg.key_limit) ? 0xFFFFFFFEu : (uint32_t)r;
+  }
+  static __device__ __forceinline__ int bin(In v, const BucketParams& P, const BucketSeg& sg, int shift) {
+    return (int)((conv(v, P, sg) >> shift) & (uint32_t)(P.nbins - 1));
+  }
+};
+
+// int64 global id -> (owner << lbits) | local row: the requester-side sort of the
+// sharded path groups the ids by owner rank first and by row inside an owner
+// (owner = id % W, local row = id / W, embedding/sharding.py:182-189), so unique
+// ids come out already partitioned.  P.p = W.
+struct RadixCompositeTraits {
+  using In = int64_t;
+  using Out = uint32_t;
+  static constexpr bool kRadix = true;
+  static __device__ __forceinline__ Out conv(In v, const BucketParams& P, const BucketSeg& sg) {
+    if (v == INT64_MIN) return 0xFFFFFFFFu;
+    if (v < 0) return 0xFFFFFFFEu;
+    uint64_t own, r;
+    if (P.div_shift >= 0) { own = (uint64_t)v & (uint64_t)(P.p - 1); r = (uint64_t)v >> P.div_shift; }
+    else { own = (uint64_t)v % (uint64_t)P.p; r = (uint64_t)v / (uint64_t)P.p; }
+    if (r >= (uint64_t)sg.key_limit) return 0xFFFFFFFEu;
+    return (uint32_t)((own << sg.lbits) | r);
+  }
+  static __device__ __forceinline__ int bin(In v, const BucketParams& P, const BucketSeg& sg, int shift) {
+    return (int)((conv(v, P, sg) >> shift) & (uint32_t)(P.nbins - 1));
+  }
+};
+
+// uint32 keys given directly (owner side of the sharded path: local rows received
+// from the requesters); keys >= key_limit are invalid.
+struct RadixDirectTraits {
+  using In = uint32_t;
+  using Out = uint32_t;
+  static constexpr bool kRadix = true;
+  static __device__ __forceinline__ Out conv(In v, const BucketParams&, const BucketSeg& sg) {
+    if (v == 0xFFFFFFFFu) return v;
+    return v >= sg.key_limit ? 0xFFFFFFFEu : v;
   }
   static __device__ __forceinline__ int bin(In v, const BucketParams& P, const BucketSeg& sg, int shift) {
     return (int)((conv(v, P, sg) >> shift) & (uint32_t)(P.nbins - 1));

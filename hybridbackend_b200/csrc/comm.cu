@@ -23,22 +23,36 @@
 //            (outputs are caller-allocated and not peer-mapped).
 // The window is used in two halves alternating per call, which is what makes a
 // trailing barrier unnecessary (see DESIGN.md "window reuse").
+#include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <string>
 
 #include "comm.cuh"
 
 namespace hb {
 
 // ---- barrier -----------------------------------------------------------------
-__global__ void barrier_kernel(PeerPtrs peers, int me, int world, uint32_t epoch) {
+// Two kernels (arrive, then wait): see comm_submit -- a kernel that publishes
+// never waits, so an in-process group can issue all arrivals before any wait.
+__global__ void barrier_arrive_kernel(PeerPtrs peers, int me, int world, uint32_t epoch) {
   const int q = threadIdx.x;
   if (q < world) {
     __threadfence_system();
     Control* remote = reinterpret_cast<Control*>(peers.p[q]);
     st_release_sys_u32(&remote->barrier_flags[me], epoch);
+  }
+}
+__global__ void barrier_wait_kernel(PeerPtrs peers, int me, int world, uint32_t epoch,
+                                    int32_t* status) {
+  const int q = threadIdx.x;
+  if (q < world) {
     Control* mine = reinterpret_cast<Control*>(peers.p[me]);
-    wait_flag(&mine->barrier_flags[q], epoch);
+    if (!wait_flag(&mine->barrier_flags[q], epoch)) raise_status(status, HB_STATUS_PEER_TIMEOUT);
   }
 }
 
@@ -49,11 +63,10 @@ struct SizesParams {
 };
 
 __global__ void __launch_bounds__(256)
-a2a_sizes_kernel(const __grid_constant__ SizesParams P, PeerPtrs peers, int me, int world, int n,
-                 uint32_t call, int slot, uint64_t half_bytes) {
+a2a_sizes_publish_kernel(const __grid_constant__ SizesParams P, PeerPtrs peers, int me, int world,
+                         int n, uint32_t call) {
   const int parity = call & 1;
-  Control* mine = reinterpret_cast<Control*>(peers.p[me]);
-  // 1. publish my N x W send sizes into every peer's mailbox row `me`
+  // publish my N x W send sizes into every peer's mailbox row `me`
   for (int i = threadIdx.x; i < n * world; i += blockDim.x) {
     const int k = i / world, r = i % world;
     const int32_t v = P.send_sizes[k][r];
@@ -62,15 +75,25 @@ a2a_sizes_kernel(const __grid_constant__ SizesParams P, PeerPtrs peers, int me, 
       remote->mailbox[parity][(me * kMaxA2aTensors + k) * kMaxWorld + r] = v;
     }
   }
-  __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < world) {
+    __threadfence_system();
     Control* remote = reinterpret_cast<Control*>(peers.p[threadIdx.x]);
     st_release_sys_u32(&remote->sizes_flags[parity][me], call);
-    wait_flag(&mine->sizes_flags[parity][threadIdx.x], call);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+a2a_sizes_collect_kernel(const __grid_constant__ SizesParams P, PeerPtrs peers, int me, int world,
+                         int n, uint32_t call, int slot, int32_t* status) {
+  const int parity = call & 1;
+  Control* mine = reinterpret_cast<Control*>(peers.p[me]);
+  if ((int)threadIdx.x < world) {
+    if (!wait_flag(&mine->sizes_flags[parity][threadIdx.x], call))
+      raise_status(status, HB_STATUS_PEER_TIMEOUT);
   }
   __syncthreads();
-  // 2. snapshot the matrix
+  // snapshot the matrix
   Snapshot* S = &mine->snap[slot];
   for (int i = threadIdx.x; i < world * n * world; i += blockDim.x) {
     const int q = i / (n * world), k = (i / world) % n, r = i % world;
@@ -78,14 +101,13 @@ a2a_sizes_kernel(const __grid_constant__ SizesParams P, PeerPtrs peers, int me, 
     S->matrix[idx] = *reinterpret_cast<volatile int32_t*>(&mine->mailbox[parity][idx]);
   }
   __syncthreads();
-  // 3. recv sizes for the caller
+  // recv sizes for the caller
   for (int i = threadIdx.x; i < n * world; i += blockDim.x) {
     const int k = i / world, q = i % world;
     const int32_t v = S->matrix[(q * kMaxA2aTensors + k) * kMaxWorld + me];
     S->recv_sizes[k * world + q] = v;
     if (P.recv_sizes[k] != nullptr) P.recv_sizes[k][q] = v;
   }
-  (void)half_bytes;
 }
 
 // Build the segment tables once row sizes (bytes per element row) are known:
@@ -193,9 +215,29 @@ struct PushParams {
   const unsigned char* inputs[kMaxA2aTensors];
 };
 
+// last-CTA-done: the CTA that finishes last publishes `epoch` into
+// data_flags[half][me] of every peer
+__device__ __forceinline__ void publish_window(PeerPtrs& peers, Control* mine, int me, int world,
+                                               int half, uint32_t epoch) {
+  __syncthreads();
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned done = atomicAdd(&mine->done_counter[half], 1u);
+    s_last = (done == gridDim.x - 1);
+    if (s_last) mine->done_counter[half] = 0;
+  }
+  __syncthreads();
+  if (s_last && (int)threadIdx.x < world) {
+    __threadfence_system();
+    Control* remote = reinterpret_cast<Control*>(peers.p[threadIdx.x]);
+    st_release_sys_u32(&remote->data_flags[half][me], epoch);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 a2a_push_kernel(const __grid_constant__ PushParams P, PeerPtrs peers, int me, int world, int n,
-                int slot, int half, uint64_t window_off, uint64_t half_bytes, uint32_t call) {
+                int slot, int half, uint64_t window_off, uint64_t half_bytes, uint32_t epoch) {
   Control* mine = reinterpret_cast<Control*>(peers.p[me]);
   const Snapshot* S = &mine->snap[slot];
   const int nseg = n * world;
@@ -211,21 +253,7 @@ a2a_push_kernel(const __grid_constant__ PushParams P, PeerPtrs peers, int me, in
                  peers.p[r] + window_off + (uint64_t)half * half_bytes + e.dst_off + o, len);
     }
   }
-  // publish: the last CTA to finish releases the epoch flag on every peer
-  __syncthreads();
-  __shared__ bool s_last;
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    const unsigned done = atomicAdd(&mine->done_counter[half], 1u);
-    s_last = (done == gridDim.x - 1);
-    if (s_last) mine->done_counter[half] = 0;
-  }
-  __syncthreads();
-  if (s_last && (int)threadIdx.x < world) {
-    __threadfence_system();
-    Control* remote = reinterpret_cast<Control*>(peers.p[threadIdx.x]);
-    st_release_sys_u32(&remote->data_flags[half][me], call);
-  }
+  publish_window(peers, mine, me, world, half, epoch);
 }
 
 struct PullParams {
@@ -234,14 +262,21 @@ struct PullParams {
 
 __global__ void __launch_bounds__(256)
 a2a_copyout_kernel(const __grid_constant__ PullParams P, PeerPtrs peers, int me, int world, int n,
-                   int slot, int half, uint64_t window_off, uint64_t half_bytes, uint32_t call) {
+                   int slot, int half, uint64_t window_off, uint64_t half_bytes, uint32_t epoch,
+                   int32_t* status) {
   Control* mine = reinterpret_cast<Control*>(peers.p[me]);
+  __shared__ int s_timeout;
+  if (threadIdx.x == 0) s_timeout = 0;
+  __syncthreads();
   if ((int)threadIdx.x < world) {
-    wait_flag(&mine->data_flags[half][threadIdx.x], call);
+    if (!wait_flag(&mine->data_flags[half][threadIdx.x], epoch)) {
+      s_timeout = 1;
+      raise_status(status, HB_STATUS_PEER_TIMEOUT);
+    }
   }
   __syncthreads();
   const Snapshot* S = &mine->snap[slot];
-  if (S->overflow) return;
+  if (S->overflow || s_timeout) return;  // never copy out data that did not arrive
   const int nseg = n * world;
   const uint64_t total = S->pull_chunks;
   const unsigned char* win = peers.p[me] + window_off + (uint64_t)half * half_bytes;
@@ -253,6 +288,160 @@ a2a_copyout_kernel(const __grid_constant__ PullParams P, PeerPtrs peers, int me,
     const uint64_t len = (e.bytes - o < kChunkBytes) ? e.bytes - o : kChunkBytes;
     copy_chunk(win + e.src_off + o, P.outputs[k] + e.dst_off + o, len);
   }
+}
+
+// ---- small dense all-reduce (sum, fp32) over the peer windows ---------------------
+// Replaces Collective.allreduce for the dense gradients of replicated small
+// tables (training/gradient.py:157-160): every rank stores its vector into slot
+// `me` of every peer's window half (an all-gather over NVSwitch), then reduces the
+// W slots locally in RANK ORDER -- the same summation order on every rank, so
+// replicas stay bit-identical -- and scales by `scale` (the reference's 1/W mean,
+// gradient.py:77-97).  W x the bytes of a ring all-reduce: meant for the small
+// replicated tables of the embedding path, not for dense model gradients.
+__global__ void __launch_bounds__(256)
+ar_push_kernel(const float* __restrict__ in, int64_t count, uint64_t slot_bytes, PeerPtrs peers,
+               int me, int world, int half, uint64_t window_off, uint64_t half_bytes,
+               uint32_t epoch) {
+  Control* mine = reinterpret_cast<Control*>(peers.p[me]);
+  const uint64_t bytes = (uint64_t)count * 4;
+  const uint64_t chunks = (bytes + kChunkBytes - 1) / kChunkBytes;
+  for (uint64_t w = blockIdx.x; w < chunks * world; w += gridDim.x) {
+    const int r = (int)(w / chunks);
+    const uint64_t o = (w % chunks) * kChunkBytes;
+    const uint64_t len = (bytes - o < kChunkBytes) ? bytes - o : kChunkBytes;
+    copy_chunk(reinterpret_cast<const unsigned char*>(in) + o,
+               peers.p[r] + window_off + (uint64_t)half * half_bytes + (uint64_t)me * slot_bytes + o,
+               len);
+  }
+  publish_window(peers, mine, me, world, half, epoch);
+}
+
+__global__ void __launch_bounds__(256)
+ar_reduce_kernel(float* __restrict__ out, int64_t count, uint64_t slot_bytes, float scale,
+                 PeerPtrs peers, int me, int world, int half, uint64_t window_off,
+                 uint64_t half_bytes, uint32_t epoch, int32_t* status) {
+  Control* mine = reinterpret_cast<Control*>(peers.p[me]);
+  __shared__ int s_timeout;
+  if (threadIdx.x == 0) s_timeout = 0;
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    if (!wait_flag(&mine->data_flags[half][threadIdx.x], epoch)) {
+      s_timeout = 1;
+      raise_status(status, HB_STATUS_PEER_TIMEOUT);
+    }
+  }
+  __syncthreads();
+  if (s_timeout) return;
+  const unsigned char* win = peers.p[me] + window_off + (uint64_t)half * half_bytes;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = reinterpret_cast<const float*>(win)[i];  // plain loads: written by peers
+    for (int q = 1; q < world; ++q)
+      acc = __fadd_rn(acc, reinterpret_cast<const float*>(win + (uint64_t)q * slot_bytes)[i]);
+    out[i] = __fmul_rn(acc, scale);
+  }
+}
+
+// ---- in-process group ---------------------------------------------------------------
+// W communicators on ONE device whose "peer" pointers are each other's
+// allocations.  One host thread per rank drives its communicator exactly as a
+// process would; collective entry points rendezvous here (comm_submit).
+struct LocalGroup {
+  std::mutex mu;
+  std::condition_variable cv;
+  int world = 0;
+  int device = 0;
+  int refs = 0;
+  hbComm* members[kMaxWorld] = {};
+  // rendezvous of the current op
+  uint64_t seq = 0;
+  int arrived = 0;
+  struct Pending {
+    const PhaseFn* run;
+    cudaStream_t stream;
+    int op_code, nphases;
+  } pend[kMaxWorld] = {};
+  int result = HB_OK;
+  std::string error;
+  cudaEvent_t ev[kMaxWorld] = {};
+  bool have_events = false;
+};
+
+static int group_flush(LocalGroup* g) {
+  const int W = g->world;
+  int nph = g->pend[0].nphases;
+  bool same_stream = true;
+  for (int r = 0; r < W; ++r) {
+    if (g->pend[r].op_code != g->pend[0].op_code || g->pend[r].nphases != nph) {
+      set_last_error("in-process group: ranks submitted different collectives (op %d/%d phases vs op %d/%d phases on rank %d)",
+                     g->pend[0].op_code, nph, g->pend[r].op_code, g->pend[r].nphases, r);
+      return HB_ERR_COMM;
+    }
+    if (g->pend[r].stream != g->pend[0].stream) same_stream = false;
+  }
+  if (!same_stream && !g->have_events) {
+    for (int r = 0; r < W; ++r) HB_CUDA_OK(cudaEventCreateWithFlags(&g->ev[r], cudaEventDisableTiming));
+    g->have_events = true;
+  }
+  for (int p = 0; p < nph; ++p) {
+    for (int r = 0; r < W; ++r) {
+      const int rc = (*g->pend[r].run)(p);
+      if (rc != HB_OK) return rc;
+    }
+    if (!same_stream && p + 1 < nph) {
+      // phase fence: every rank's next phase is ordered behind all ranks' phase p
+      for (int r = 0; r < W; ++r) HB_CUDA_OK(cudaEventRecord(g->ev[r], g->pend[r].stream));
+      for (int r = 0; r < W; ++r)
+        for (int q = 0; q < W; ++q)
+          if (q != r) HB_CUDA_OK(cudaStreamWaitEvent(g->pend[r].stream, g->ev[q], 0));
+    }
+  }
+  return HB_OK;
+}
+
+int comm_submit(hbComm* c, int op_code, int nphases, cudaStream_t stream, const PhaseFn& run) {
+  LocalGroup* g = c->group;
+  if (g == nullptr) {
+    for (int p = 0; p < nphases; ++p) {
+      const int rc = run(p);
+      if (rc != HB_OK) return rc;
+    }
+    return HB_OK;
+  }
+  std::unique_lock<std::mutex> lk(g->mu);
+  const uint64_t my_seq = g->seq;
+  g->pend[c->rank] = LocalGroup::Pending{&run, stream, op_code, nphases};
+  g->arrived++;
+  if (g->arrived == g->world) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != g->device) cudaSetDevice(g->device);
+    g->result = group_flush(g);
+    if (g->result != HB_OK) g->error = get_last_error();
+    if (dev != g->device) cudaSetDevice(dev);
+    g->arrived = 0;
+    g->seq++;
+    g->cv.notify_all();
+    return g->result;
+  }
+  // the submitting thread stays here until the last rank has issued everything:
+  // `run` (and what it captures by reference) must stay alive, and the entry
+  // point's contract is that the work is enqueued when it returns
+  static const int timeout_s = [] {
+    const char* e = getenv("HB_LOCAL_GROUP_TIMEOUT_S");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 120;
+  }();
+  const bool ok = g->cv.wait_for(lk, std::chrono::seconds(timeout_s), [&] { return g->seq != my_seq; });
+  if (!ok) {
+    g->arrived--;
+    set_last_error("in-process group: rank %d waited %d s for the other ranks to submit op %d "
+                   "(every rank must issue the same collective sequence, one thread per rank)",
+                   c->rank, timeout_s, op_code);
+    return HB_ERR_COMM;
+  }
+  if (g->result != HB_OK) set_last_error("%s", g->error.c_str());
+  return g->result;
 }
 
 }  // namespace hb
@@ -330,12 +519,63 @@ int hbCommConnect(hbComm* c, const unsigned char* all_tokens) {
   return HB_OK;
 }
 
+int hbCommCreateLocalGroup(int world_size, size_t window_bytes, hbComm** comms) {
+  using namespace hb;
+  HB_REQUIRE(comms, "hbCommCreateLocalGroup: null argument");
+  HB_REQUIRE(world_size >= 1 && world_size <= kMaxWorld,
+             "hbCommCreateLocalGroup: world_size %d not in [1,%d]", world_size, kMaxWorld);
+  LocalGroup* g = new LocalGroup();
+  g->world = world_size;
+  HB_CUDA_OK(cudaGetDevice(&g->device));
+  for (int r = 0; r < world_size; ++r) {
+    hbComm* c = new hbComm();
+    memset(c, 0, sizeof(*c));
+    c->rank = r; c->world = world_size; c->local = world_size;
+    c->window_bytes = align_up(window_bytes, 4096);
+    c->alloc_bytes = control_bytes() + c->window_bytes;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->base), c->alloc_bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->base, 0, control_bytes());
+    if (e != cudaSuccess) {
+      set_last_error("hbCommCreateLocalGroup: allocating rank %d (%zu B) failed: %s", r, c->alloc_bytes,
+                     cudaGetErrorString(e));
+      if (c->base) cudaFree(c->base);
+      delete c;
+      for (int q = 0; q < r; ++q) { cudaFree(g->members[q]->base); delete g->members[q]; }
+      delete g;
+      return HB_ERR_CUDA;
+    }
+    c->group = g;
+    g->members[r] = c;
+  }
+  for (int r = 0; r < world_size; ++r) {
+    for (int q = 0; q < world_size; ++q) g->members[r]->peer[q] = g->members[q]->base;
+    g->members[r]->connected = true;
+    comms[r] = g->members[r];
+  }
+  g->refs = world_size;
+  cudaDeviceSynchronize();
+  return HB_OK;
+}
+
 int hbCommDestroy(hbComm* c) {
   if (!c) return HB_OK;
   cudaDeviceSynchronize();
   for (int q = 0; q < c->world; ++q)
     if (c->opened[q]) cudaIpcCloseMemHandle(c->peer[q]);
   if (c->base) cudaFree(c->base);
+  if (c->group != nullptr) {
+    hb::LocalGroup* g = c->group;
+    bool last;
+    {
+      std::lock_guard<std::mutex> lk(g->mu);
+      last = (--g->refs == 0);
+    }
+    if (last) {
+      if (g->have_events)
+        for (int r = 0; r < g->world; ++r) cudaEventDestroy(g->ev[r]);
+      delete g;
+    }
+  }
   delete c;
   return HB_OK;
 }
@@ -345,14 +585,24 @@ int hbCommWorldSize(const hbComm* c) { return c ? c->world : -1; }
 void* hbCommWindow(hbComm* c) { return c ? c->base + hb::control_bytes() : nullptr; }
 size_t hbCommWindowBytes(const hbComm* c) { return c ? c->window_bytes : 0; }
 
-int hbCommBarrier(hbComm* c, hbStream stream) {
-  using namespace hb;
-  HB_REQUIRE(c && c->connected, "hbCommBarrier: communicator not connected");
-  c->barrier_epoch++;
-  KernelScope ks(HB_K_BARRIER, (cudaStream_t)stream);
-  barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(peer_ptrs(c), c->rank, c->world, c->barrier_epoch);
-  HB_CUDA_OK(cudaGetLastError());
+int hbCommSetStatusWord(hbComm* c, int32_t* d_status) {
+  HB_REQUIRE(c, "hbCommSetStatusWord: null communicator");
+  c->d_status = d_status;
   return HB_OK;
+}
+
+int hbCommBarrier(hbComm* c, hbStream stream_) {
+  using namespace hb;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  HB_REQUIRE(c && c->connected, "hbCommBarrier: communicator not connected");
+  const uint32_t epoch = ++c->barrier_epoch;
+  return comm_submit(c, kOpBarrier, 2, stream, [&](int phase) -> int {
+    KernelScope ks(HB_K_BARRIER, stream);
+    if (phase == 0) barrier_arrive_kernel<<<1, 32, 0, stream>>>(peer_ptrs(c), c->rank, c->world, epoch);
+    else barrier_wait_kernel<<<1, 32, 0, stream>>>(peer_ptrs(c), c->rank, c->world, epoch, c->d_status);
+    HB_CUDA_OK(cudaGetLastError());
+    return HB_OK;
+  });
 }
 
 int hbAlltoallvNSizes(hbComm* c, int n, const int32_t* const* d_send_sizes,
@@ -373,18 +623,26 @@ int hbAlltoallvNSizes(hbComm* c, int n, const int32_t* const* d_send_sizes,
   const uint32_t call = ++c->sizes_calls;
   const int slot = call % kSnapSlots;
   c->n_of_call[slot] = n;
-  {
-    KernelScope ks(HB_K_A2A_SIZES, stream);
-    a2a_sizes_kernel<<<1, 256, 0, stream>>>(P, peer_ptrs(c), c->rank, c->world, n, call, slot,
-                                             c->window_bytes / 2);
-  }
-  HB_CUDA_OK(cudaGetLastError());
-  if (h_recv_sizes != nullptr) {
-    Control* ctl = reinterpret_cast<Control*>(c->base);
-    HB_CUDA_OK(cudaMemcpyAsync(h_recv_sizes, ctl->snap[slot].recv_sizes,
-                               sizeof(int32_t) * (size_t)n * c->world, cudaMemcpyDeviceToHost, stream));
-  }
-  return HB_OK;
+  return comm_submit(c, kOpA2aSizes, 2, stream, [&](int phase) -> int {
+    if (phase == 0) {
+      KernelScope ks(HB_K_A2A_SIZES, stream);
+      a2a_sizes_publish_kernel<<<1, 256, 0, stream>>>(P, peer_ptrs(c), c->rank, c->world, n, call);
+      HB_CUDA_OK(cudaGetLastError());
+      return HB_OK;
+    }
+    {
+      KernelScope ks(HB_K_A2A_SIZES, stream);
+      a2a_sizes_collect_kernel<<<1, 256, 0, stream>>>(P, peer_ptrs(c), c->rank, c->world, n, call, slot,
+                                                       c->d_status);
+    }
+    HB_CUDA_OK(cudaGetLastError());
+    if (h_recv_sizes != nullptr) {
+      Control* ctl = reinterpret_cast<Control*>(c->base);
+      HB_CUDA_OK(cudaMemcpyAsync(h_recv_sizes, ctl->snap[slot].recv_sizes,
+                                 sizeof(int32_t) * (size_t)n * c->world, cudaMemcpyDeviceToHost, stream));
+    }
+    return HB_OK;
+  });
 }
 
 int hbAlltoallvN(hbComm* c, int n, const void* const* d_inputs, const int64_t* common_sizes,
@@ -408,29 +666,71 @@ int hbAlltoallvN(hbComm* c, int n, const void* const* d_inputs, const int64_t* c
     PP.inputs[k] = reinterpret_cast<const unsigned char*>(d_inputs[k]);
     QP.outputs[k] = reinterpret_cast<unsigned char*>(d_outputs[k]);
   }
-  c->data_calls = call;
-  const int half = call & 1;
   HB_REQUIRE(c->window_bytes > c->reserved_bytes, "hbAlltoallvN: no window space left beside the sharded plan");
+  c->data_calls = call;
+  const uint32_t epoch = ++c->win_seq;
+  const int half = epoch & 1;
   const uint64_t half_bytes = ((c->window_bytes - c->reserved_bytes) / 2) & ~(uint64_t)255;
   const uint64_t woff = control_bytes() + c->reserved_bytes;
-  PeerPtrs pp = peer_ptrs(c);
-  {
-    KernelScope ks(HB_K_A2A_TABLES, stream);
-    a2a_tables_kernel<<<1, 256, 0, stream>>>(T, pp, c->rank, c->world, n, slot, half_bytes, d_status);
-  }
-  HB_CUDA_OK(cudaGetLastError());
+  if (d_status == nullptr) d_status = c->d_status;
   const int grid = device_sm_count() * 2;
-  {
-    KernelScope ks(HB_K_A2A_PUSH, stream);
-    a2a_push_kernel<<<grid, 256, 0, stream>>>(PP, pp, c->rank, c->world, n, slot, half, woff, half_bytes, call);
-  }
-  HB_CUDA_OK(cudaGetLastError());
-  {
+  return comm_submit(c, kOpA2aData, 2, stream, [&](int phase) -> int {
+    PeerPtrs pp = peer_ptrs(c);
+    if (phase == 0) {
+      {
+        KernelScope ks(HB_K_A2A_TABLES, stream);
+        a2a_tables_kernel<<<1, 256, 0, stream>>>(T, pp, c->rank, c->world, n, slot, half_bytes, d_status);
+      }
+      HB_CUDA_OK(cudaGetLastError());
+      KernelScope ks(HB_K_A2A_PUSH, stream);
+      a2a_push_kernel<<<grid, 256, 0, stream>>>(PP, pp, c->rank, c->world, n, slot, half, woff, half_bytes, epoch);
+      HB_CUDA_OK(cudaGetLastError());
+      return HB_OK;
+    }
     KernelScope ks(HB_K_A2A_COPYOUT, stream);
-    a2a_copyout_kernel<<<grid, 256, 0, stream>>>(QP, pp, c->rank, c->world, n, slot, half, woff, half_bytes, call);
+    a2a_copyout_kernel<<<grid, 256, 0, stream>>>(QP, pp, c->rank, c->world, n, slot, half, woff, half_bytes,
+                                                  epoch, d_status);
+    HB_CUDA_OK(cudaGetLastError());
+    return HB_OK;
+  });
+}
+
+int hbAllreduceSumF32(hbComm* c, const float* d_in, float* d_out, int64_t count, float scale,
+                      int32_t* d_status, hbStream stream_) {
+  using namespace hb;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  HB_REQUIRE(c && c->connected, "hbAllreduceSumF32: communicator not connected");
+  HB_REQUIRE(count >= 0 && (count == 0 || (d_in && d_out)), "hbAllreduceSumF32: bad arguments");
+  HB_REQUIRE(c->window_bytes > c->reserved_bytes, "hbAllreduceSumF32: no window space left beside the sharded plan");
+  const uint64_t half_bytes = ((c->window_bytes - c->reserved_bytes) / 2) & ~(uint64_t)255;
+  const uint64_t slot_bytes = align_up((size_t)count * 4, 256);
+  if (slot_bytes * (uint64_t)c->world > half_bytes) {
+    set_last_error("hbAllreduceSumF32: %lld floats x %d ranks need %llu B, window half is %llu B",
+                   (long long)count, c->world, (unsigned long long)(slot_bytes * c->world),
+                   (unsigned long long)half_bytes);
+    return HB_ERR_WORKSPACE;
   }
-  HB_CUDA_OK(cudaGetLastError());
-  return HB_OK;
+  const uint32_t epoch = ++c->win_seq;
+  const int half = epoch & 1;
+  const uint64_t woff = control_bytes() + c->reserved_bytes;
+  if (d_status == nullptr) d_status = c->d_status;
+  const uint64_t chunks = ((uint64_t)count * 4 + kChunkBytes - 1) / kChunkBytes * c->world;
+  const int maxg = device_sm_count() * 2;
+  const int grid_push = chunks < 1 ? 1 : (chunks < (uint64_t)maxg ? (int)chunks : maxg);
+  const int64_t rb = (count + 255) / 256;
+  const int grid_red = rb < 1 ? 1 : (rb < maxg ? (int)rb : maxg);
+  return comm_submit(c, kOpAllreduce, 2, stream, [&](int phase) -> int {
+    PeerPtrs pp = peer_ptrs(c);
+    KernelScope ks(phase == 0 ? HB_K_AR_PUSH : HB_K_AR_REDUCE, stream);
+    if (phase == 0)
+      ar_push_kernel<<<grid_push, 256, 0, stream>>>(d_in, count, slot_bytes, pp, c->rank, c->world, half, woff,
+                                                    half_bytes, epoch);
+    else
+      ar_reduce_kernel<<<grid_red, 256, 0, stream>>>(d_out, count, slot_bytes, scale, pp, c->rank, c->world,
+                                                     half, woff, half_bytes, epoch, d_status);
+    HB_CUDA_OK(cudaGetLastError());
+    return HB_OK;
+  });
 }
 
 }  // extern "C"

@@ -1,6 +1,9 @@
 // comm.cuh -- shared definitions of the NVSwitch peer-memory communicator
-// (control block layout, flags, hbComm) used by comm.cu and sharded.cu.
+// (control block layout, flags, hbComm, phased submission) used by comm.cu and
+// sharded.cu.
 #pragma once
+#include <functional>
+
 #include "common.cuh"
 
 namespace hb {
@@ -28,7 +31,7 @@ struct Snapshot {
 struct Control {
   uint32_t barrier_flags[kMaxWorld];                // epoch of last barrier seen from q
   uint32_t sizes_flags[2][kMaxWorld];               // per mailbox parity
-  uint32_t data_flags[2][kMaxWorld];                // per window half
+  uint32_t data_flags[2][kMaxWorld];                // per window half (alltoallv payload, allreduce)
   uint32_t plan_flags[8][kMaxWorld];                // sharded-plan phases (sharded.cu)
   uint32_t done_counter[8];                         // last-CTA-done counters
   int32_t mailbox[2][kMaxWorld * kMaxA2aTensors * kMaxWorld];  // [parity][q][k][r]
@@ -37,6 +40,8 @@ struct Control {
 };
 
 constexpr uint64_t kChunkBytes = 16384;
+
+struct LocalGroup;  // in-process rendezvous of W communicators on one device (comm.cu)
 
 }  // namespace hb
 
@@ -52,7 +57,11 @@ struct hbComm {
   uint32_t barrier_epoch;
   uint32_t sizes_calls;  // number of hbAlltoallvNSizes issued
   uint32_t data_calls;   // number of hbAlltoallvN issued
+  uint32_t win_seq;      // window-half users so far (alltoallv payloads + allreduces)
+  uint32_t plan_epoch;   // sharded-plan steps issued on this communicator (monotonic ACROSS plans)
   int n_of_call[hb::kSnapSlots];
+  int32_t* d_status;     // optional sticky status word for kernels of ops without one
+  hb::LocalGroup* group; // != nullptr: member of an in-process group
   cudaIpcMemHandle_t handle;
 };
 
@@ -74,5 +83,23 @@ static inline PeerPtrs peer_ptrs(const hbComm* c) {
 __device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t epoch) {
   return spin_until(flag, epoch);
 }
+
+// A collective is a fixed sequence of PHASES per rank.  Kernels of phase p only
+// spin on flags that kernels of phases < p (of any rank, same or earlier op)
+// publish, and a phase that publishes never waits.  A multi-process
+// communicator runs the phases back to back on `stream` (the spins resolve as the
+// peers' kernels run on their GPUs).  A member of an in-process group blocks
+// until every rank of the group has submitted the same op; the last arrival
+// then issues all ranks' phases phase-major (with event fences when the ranks
+// use different streams), so that on ONE device no kernel ever spins on a flag
+// whose producer has not been launched.  op_code identifies the op for the
+// rendezvous sanity check.
+using PhaseFn = std::function<int(int phase)>;
+int comm_submit(hbComm* c, int op_code, int nphases, cudaStream_t stream, const PhaseFn& run);
+
+enum { kOpBarrier = 1, kOpA2aSizes = 2, kOpA2aData = 3, kOpAllreduce = 4,
+       kOpShardedFwd = 5, kOpShardedBwd = 6 };
+
+const char* get_last_error();
 
 }  // namespace hb

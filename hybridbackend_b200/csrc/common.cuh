@@ -137,9 +137,4 @@ __device__ __forceinline__ void raise_status(int32_t* status, int32_t bit) {
 int lookup_forward_run(int n, const hbLookupFeature* feats, const int32_t* const* idx32,
                        const WaitSpec* wait, bool coherent, int32_t* d_status,
                        cudaStream_t stream, int kernel_id);
-// sparse_update.cu
-int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* opt, void* ws,
-                      size_t ws_bytes, int32_t* d_status, cudaStream_t stream,
-                      const WaitSpec* wait, const int32_t* const* n_dev, int phases = 3);
-
 }  // namespace hb

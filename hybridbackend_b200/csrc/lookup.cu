@@ -28,6 +28,7 @@ struct LookupFeat {
   int64_t rows;
   int64_t out_stride;
   int64_t id_div;
+  int64_t nnz;
   int32_t nbags;
   int32_t dim;
   int32_t combiner;
@@ -177,7 +178,7 @@ lookup_fwd_kernel(const __grid_constant__ LookupParams P) {
         if (b >= nbags) break;
         int64_t s = F.offsets[b];
         int64_t e = F.offsets[b + 1];
-        if (e < s || s < 0) { bad_off = true; e = s; }
+        if (e < s || s < 0 || e > F.nnz) { bad_off = true; e = s; }
         float4 acc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -280,6 +281,8 @@ static int validate_feature(int k, const hbLookupFeature& f, bool has_idx32) {
              "lookup: feature %d out_stride %lld must be a multiple of 4 and >= dim", k,
              (long long)f.out_stride);
   HB_REQUIRE(f.combiner >= HB_SUM && f.combiner <= HB_SQRTN, "lookup: feature %d bad combiner", k);
+  HB_REQUIRE(f.nnz >= 0 && (f.offsets != nullptr || f.nnz == f.nbags),
+             "lookup: feature %d nnz %lld must be the id count (== nbags without offsets)", k, (long long)f.nnz);
   if (f.nbags > 0) {
     HB_REQUIRE(f.table && (f.ids || has_idx32) && f.out, "lookup: feature %d null pointer", k);
     HB_REQUIRE(((uintptr_t)f.table & 15) == 0 && ((uintptr_t)f.out & 15) == 0,
@@ -328,7 +331,7 @@ int lookup_forward_run(int n, const hbLookupFeature* feats, const int32_t* const
       LookupFeat& F = P.f[P.nfeats];
       F.table = f.table; F.ids = f.ids; F.offsets = f.offsets; F.out = f.out;
       F.idx32 = idx32 ? idx32[k] : nullptr;
-      F.rows = f.rows; F.out_stride = f.out_stride; F.id_div = f.id_div;
+      F.rows = f.rows; F.out_stride = f.out_stride; F.id_div = f.id_div; F.nnz = f.nnz;
       F.nbags = (int32_t)f.nbags; F.dim = f.dim; F.combiner = f.combiner;
       F.div_shift = ((f.id_div & (f.id_div - 1)) == 0) ? ilog2_ceil((int)f.id_div) : -1;
       if (f.id_div > (1 << 30)) F.div_shift = -1;

@@ -12,6 +12,8 @@ namespace hb {
 
 static thread_local char g_last_error[1024] = "";
 
+const char* get_last_error() { return g_last_error; }
+
 void set_last_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -65,7 +67,8 @@ static const char* kKernelNames[HB_K_COUNT] = {
     "", "bag_of_position", "lookup_fwd", "sparse_update", "sparse_update_fixup",
     "cast_n", "cache_lookup", "barrier", "a2a_sizes", "a2a_tables", "a2a_push", "a2a_copyout",
     "sharded_exchange", "sharded_push_ids", "sharded_owner_gather", "sharded_stitch_pool",
-    "sharded_push_grads", "sharded_pad"};
+    "sharded_push_grads", "sharded_pad", "allreduce_push", "allreduce_reduce", "update_runs",
+    "sparse_update_long", "sharded_publish", "sharded_unique", "h2d_stage", ""};
 
 }  // namespace hb
 

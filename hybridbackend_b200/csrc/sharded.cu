@@ -1,26 +1,33 @@
-// sharded.cu -- the fused sharded GroupLookup over NVSwitch peer memory:
-// K1 partition + K2 id push + K3 owner gather fused with the row push (the
-// return all-to-all) + K4 stitch/pool, and the backward gradient push fused
-// with K5 (owner-side dedup + sparse optimizer).  It is the composition of
-// embedding/sharding.py:171-203 with every intermediate kept on the device:
-// no host synchronisation, static shapes, no NCCL.
+// sharded.cu -- the fused sharded GroupLookup over NVSwitch peer memory.  It is the
+// composition of embedding/sharding.py:171-203 (partition -> alltoallv(ids) ->
+// unique -> gather -> alltoallv(rows) -> stitch) and of its backward with every
+// intermediate kept on the device: no host synchronisation, static shapes, no NCCL,
+// and only UNIQUE ids / rows / gradient sums on the wire.
 //
-// Per rank and step (forward):
-//   partition        ids --(id % W, stable)--> part_ids, sizes[W], idx      (K1)
-//   exchange         sizes all-gather through peer mailboxes; every rank derives
-//                    all offsets it needs from the W x F x W matrix          (1 CTA)
-//   push_ids         my bucket r -> owner r's ids_in window (128-bit stores) (K2)
-//   owner_gather     for every id I own: read the row of my shard (local row
-//                    id / W) and store it into the REQUESTER's rows_in window at
-//                    its partitioned position -- gather and return all-to-all
-//                    are one kernel, tile by tile over NVLink              (K3+K2')
-//   stitch_pool      out[b] = pool_p rows_in[idx[p]]                          (K4)
+// Forward, per rank and step:
+//   requester sort   ids --radix sort by (id % W, id / W)--> runs            (K1)
+//                    one scan -> unique ids grouped by owner (the partition of
+//                    HbPartitionByModulo applied to the deduplicated ids), the
+//                    inverse map position -> unique, per-owner counts
+//   publish / meta   counts all-gather through peer mailboxes; every rank derives
+//                    all offsets it needs from the W x F x W matrix
+//   push_ids         my unique local rows of owner r -> r's ids_in window      (K2)
+//   owner_gather     for every row I own that was asked for: read it from my shard
+//                    and store it into the REQUESTER's rows_in window at the slot of
+//                    its unique -- gather and return all-to-all are one kernel,
+//                    tile by tile over NVLink                                 (K3+K2')
+//   stitch_pool      out[b] = pool_p rows_in[inverse[p]]                        (K4)
 // Backward:
-//   push_grads       row gradient of position p -> owner's grads_in window at
-//                    the position its id was received                       (K2'')
-//   owner update     radix sort of the received ids + fused dedup/optimizer  (K5)
+//   emit             per unique id: sum of the row gradients of its positions (in
+//                    position order) stored straight into the owner's grads_in
+//                    window (K2'' fused with the requester half of the dedup)
+//   owner update     radix sort of the received rows + fused dedup/optimizer    (K5)
+// Requester-side dedup changes wire bytes only: the owner still adds the per-rank
+// sums of a row in rank order (training/gradient.py:216-217: no 1/W).
 // Cross-GPU ordering: epoch-valued flags (st.release.sys by the last CTA of the
-// producer kernel, ld.acquire.sys spin at the start of the consumer kernel).
+// producer kernel, ld.acquire.sys spin at the start of the consumer kernel).  A
+// producer only writes a peer's window after a flag wait that is stream-ordered
+// behind the peer's last read of it, so every window region is single-buffered.
 #include <math.h>
 #include <string.h>
 
@@ -28,56 +35,50 @@
 
 #include "bucket.cuh"
 #include "comm.cuh"
+#include "update.cuh"
 
 namespace hb {
 
-constexpr int kShMaxFeats = 64;   // features per plan launch group
-constexpr int kIdChunk = 2048;    // ids per copy chunk (16 KB)
+constexpr int kShMaxFeats = kMaxA2aTensors;  // features per plan (mailbox rows)
+constexpr int kShThreads = 256;
+constexpr int kIdChunk = 2048;               // unique ids per push work unit
 
 struct ShFeatMeta {
-  int32_t send_off[kMaxWorld + 1];    // my bucket starts in part_ids (prefix of my sizes)
+  int32_t send_off[kMaxWorld + 1];    // my bucket starts in my unique list
   int32_t remote_base[kMaxWorld];     // my segment start inside owner r's ids_in / grads_in
   int32_t recv_base[kMaxWorld + 1];   // as owner: start of source q's segment (clamped to cap)
-  int32_t src_bucket_off[kMaxWorld];  // as owner: start of bucket `me` in q's partitioned order
-  int32_t recv_total;                 // unclamped number of ids addressed to me
+  int32_t src_bucket_off[kMaxWorld];  // as owner: start of bucket `me` in q's unique list
+  int32_t recv_total;                 // unclamped number of rows asked of me
   int32_t recv_clamped;               // min(recv_total, cap): entries actually received
 };
 
+// One feature of a plan; lives in DEVICE memory (n can be in the hundreds: C4 has
+// 200 features), rewritten by one small H2D copy per call.
 struct ShFeat {
-  // static (plan)
-  int64_t* part_ids;
-  int32_t* part_idx;
-  int32_t* sizes;        // [W]
-  int32_t* bag_of_pos;   // CSR features
-  uint64_t ids_in_off[2];  // byte offsets inside the data window
+  const uint32_t* ukey;        // requester: unique composite keys (sort workspace)
+  const int32_t* counts;       // requester: [0] = number of uniques
+  const int32_t* owner_start1; // requester: [W] first unique of owner r, +1 (0: none)
+  const float* shard;          // owner: local shard
+  int64_t shard_rows;
+  uint64_t ids_in_off;         // byte offsets inside the data window
   uint64_t rows_in_off;
   uint64_t grads_in_off;
   int32_t cap;
   int32_t dim;
   int32_t log2g;
+  int32_t lbits;
   int32_t max_nnz;
-  // per call
-  const float* shard;
-  const float* grad;
-  const int64_t* offsets;
-  int64_t shard_rows;
-  int64_t grad_stride;
-  int32_t nnz;
-  int32_t nbags;
-  int32_t combiner;
-  int32_t cta_begin;
+  int32_t pad;
 };
 
 struct ShParams {
-  ShFeat f[kShMaxFeats];
+  const ShFeat* feats;   // [n] device
   ShFeatMeta* meta;      // [n] device
   PeerPtrs peers;
   uint64_t window_off;   // control_bytes()
   int32_t* status;
-  int32_t n, me, world, parity;
+  int32_t n, me, world;
   uint32_t epoch;
-  int32_t total_ctas;
-  int32_t div_shift;     // log2(W) or -1
 };
 
 __device__ __forceinline__ Control* ctl(const ShParams& P, int r) {
@@ -108,101 +109,154 @@ __device__ __forceinline__ void signal_all_peers(const ShParams& P, int phase, i
   }
 }
 
-__device__ __forceinline__ void wait_all_peers(const ShParams& P, int phase) {
-  if ((int)threadIdx.x < P.world)
-    if (!wait_flag(&ctl(P, P.me)->plan_flags[phase][threadIdx.x], P.epoch))
-      raise_status(P.status, HB_STATUS_PEER_TIMEOUT);
+// returns false (and raises the status bit) when a peer never arrived
+__device__ __forceinline__ bool wait_all_peers(const ShParams& P, int phase) {
+  __shared__ int s_timeout;
+  if (threadIdx.x == 0) s_timeout = 0;
   __syncthreads();
+  if ((int)threadIdx.x < P.world)
+    if (!wait_flag(&ctl(P, P.me)->plan_flags[phase][threadIdx.x], P.epoch)) {
+      s_timeout = 1;
+      raise_status(P.status, HB_STATUS_PEER_TIMEOUT);
+    }
+  __syncthreads();
+  return s_timeout == 0;
 }
 
-// ---- exchange: sizes all-gather + offset derivation (1 CTA) ---------------------
-__global__ void __launch_bounds__(256) sh_exchange_kernel(const __grid_constant__ ShParams P) {
+// dense work map over up to kShMaxFeats features (see sparse_update.cu seg_scan)
+__device__ __forceinline__ int sh_seg_scan(int nsegs, int my_units, int* s_begin /*[kShMaxFeats + 1]*/) {
+  if ((int)threadIdx.x < nsegs) s_begin[threadIdx.x] = my_units;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int carry = 0;
+    for (int b = 0; b < nsegs; b += 32) {
+      const int i = b + (int)threadIdx.x;
+      const int v = i < nsegs ? s_begin[i] : 0;
+      int incl = v;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, off);
+        if ((int)threadIdx.x >= off) incl += y;
+      }
+      if (i < nsegs) s_begin[i] = carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (threadIdx.x == 0) s_begin[nsegs] = carry;
+  }
+  __syncthreads();
+  return s_begin[nsegs];
+}
+__device__ __forceinline__ int sh_seg_find(const int* s_begin, int nsegs, int unit) {
+  int lo = 0, hi = nsegs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (s_begin[mid] <= unit) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// ---- publish: my per-owner unique counts -> every peer's mailbox (1 CTA) ---------------
+__global__ void __launch_bounds__(kShThreads) sh_publish_kernel(const __grid_constant__ ShParams P) {
+  const int W = P.world, me = P.me, n = P.n;
+  const int par = P.epoch & 1;
+  for (int f = threadIdx.x; f < n; f += blockDim.x) {
+    const ShFeat& F = P.feats[f];
+    // unique list is grouped by owner: bucket r = [start[r], start[r+1]); owners
+    // without ids never wrote their start
+    int nxt = F.counts[0];
+    int32_t sz[kMaxWorld];
+    for (int r = W - 1; r >= 0; --r) {
+      const int s1 = F.owner_start1[r];
+      const int st = s1 > 0 ? s1 - 1 : nxt;
+      sz[r] = nxt - st;
+      nxt = st;
+    }
+    for (int r = 0; r < W; ++r)
+      for (int q = 0; q < W; ++q)
+        ctl(P, q)->plan_mailbox[par][(me * kMaxA2aTensors + f) * kMaxWorld + r] = sz[r];
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < W) {
+    __threadfence_system();
+    st_release_sys_u32(&ctl(P, threadIdx.x)->plan_flags[0][me], P.epoch);
+  }
+}
+
+// ---- meta: offset algebra from the all-gathered W x F x W matrix (1 CTA) ---------------
+__global__ void __launch_bounds__(kShThreads) sh_meta_kernel(const __grid_constant__ ShParams P) {
   const int W = P.world, me = P.me, n = P.n;
   const int par = P.epoch & 1;
   Control* mine = ctl(P, me);
-  for (int i = threadIdx.x; i < n * W; i += blockDim.x) {
-    const int f = i / W, r = i % W;
-    const int32_t v = P.f[f].sizes[r];
-    for (int q = 0; q < W; ++q)
-      ctl(P, q)->plan_mailbox[par][(me * kMaxA2aTensors + f) * kMaxWorld + r] = v;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < W) {
-    st_release_sys_u32(&ctl(P, threadIdx.x)->plan_flags[0][me], P.epoch);
-    if (!wait_flag(&mine->plan_flags[0][threadIdx.x], P.epoch))
-      raise_status(P.status, HB_STATUS_PEER_TIMEOUT);
-  }
-  __syncthreads();
+  wait_all_peers(P, 0);
   auto S = [&](int q, int f, int r) -> int32_t {
     return *reinterpret_cast<volatile int32_t*>(
         &mine->plan_mailbox[par][(q * kMaxA2aTensors + f) * kMaxWorld + r]);
   };
   for (int f = threadIdx.x; f < n; f += blockDim.x) {
     ShFeatMeta m;
-    const int cap = P.f[f].cap;
+    const int cap = P.feats[f].cap;
     int acc = 0;
     for (int r = 0; r < W; ++r) { m.send_off[r] = acc; acc += S(me, f, r); }
-    m.send_off[W] = acc;
-    for (int r = W + 1; r <= kMaxWorld; ++r) m.send_off[r] = acc;
-    for (int r = 0; r < W; ++r) {
+    for (int r = W; r <= kMaxWorld; ++r) m.send_off[r] = acc;
+    for (int r = 0; r < kMaxWorld; ++r) {
       int b = 0;
-      for (int q = 0; q < me; ++q) b += S(q, f, r);
+      if (r < W)
+        for (int q = 0; q < me; ++q) b += S(q, f, r);
       m.remote_base[r] = b;
     }
     acc = 0;
-    for (int q = 0; q < W; ++q) {
+    for (int q = 0; q < kMaxWorld; ++q) {
       m.recv_base[q] = acc < cap ? acc : cap;
-      acc += S(q, f, me);
       int o = 0;
-      for (int r = 0; r < me; ++r) o += S(q, f, r);
+      if (q < W) {
+        acc += S(q, f, me);
+        for (int r = 0; r < me; ++r) o += S(q, f, r);
+      }
       m.src_bucket_off[q] = o;
     }
+    m.recv_base[kMaxWorld] = acc < cap ? acc : cap;
     m.recv_total = acc;
-    for (int q = W; q <= kMaxWorld; ++q) m.recv_base[q] = acc < cap ? acc : cap;
     m.recv_clamped = acc < cap ? acc : cap;
-    if (acc > cap) raise_status(P.status, HB_STATUS_WINDOW_OVERFLOW);
+    // every rank sees the whole matrix: an overflow at ANY owner is raised on EVERY
+    // rank (its requesters would otherwise read rows that were never gathered)
+    bool ovf = false;
+    for (int r = 0; r < W; ++r) {
+      int t = 0;
+      for (int q = 0; q < W; ++q) t += S(q, f, r);
+      if (t > cap) ovf = true;
+    }
+    if (ovf) raise_status(P.status, HB_STATUS_WINDOW_OVERFLOW);
     P.meta[f] = m;
   }
 }
 
-// ---- push ids ---------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sh_push_ids_kernel(const __grid_constant__ ShParams P) {
+// ---- push unique local rows to their owners -------------------------------------------
+__global__ void __launch_bounds__(kShThreads) sh_push_ids_kernel(const __grid_constant__ ShParams P) {
+  __shared__ int s_begin[kShMaxFeats + 1];
   const int W = P.world;
-  // work items: (f, r, chunk); chunk < ceil(max_nnz / kIdChunk)
-  int item = blockIdx.x;
-  for (;; item += gridDim.x) {
-    // decode item -> (f, r, c) walking features (few); total_ctas carries the item count
-    if (item >= P.total_ctas) break;
-    int f = 0, rem = item;
-    while (true) {
-      const int per = W * ((P.f[f].max_nnz + kIdChunk - 1) / kIdChunk);
-      if (rem < per) break;
-      rem -= per;
-      ++f;
-    }
-    const int chunks = (P.f[f].max_nnz + kIdChunk - 1) / kIdChunk;
-    const int r = rem / chunks, c = rem % chunks;
+  int units = 0;
+  if ((int)threadIdx.x < P.n) {
+    const int U = P.meta[threadIdx.x].send_off[W];
+    units = (U + kIdChunk - 1) / kIdChunk;
+  }
+  const int total = sh_seg_scan(P.n, units, s_begin);
+  for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    const int f = sh_seg_find(s_begin, P.n, unit);
+    const ShFeat& F = P.feats[f];
     const ShFeatMeta& m = P.meta[f];
-    const int beg = m.send_off[r] + c * kIdChunk;
-    int end = m.send_off[r + 1];
-    if (beg >= end) continue;
-    if (end > beg + kIdChunk) end = beg + kIdChunk;
-    // clamp to the owner's capacity
-    const int cap_r = P.f[f].cap;
-    const int dst0 = m.remote_base[r] + c * kIdChunk;
-    int cnt = end - beg;
-    if (dst0 + cnt > cap_r) cnt = cap_r - dst0;
-    if (cnt <= 0) continue;
-    const int64_t* src = P.f[f].part_ids + beg;
-    int64_t* dst = reinterpret_cast<int64_t*>(win(P, r) + P.f[f].ids_in_off[P.parity]) + dst0;
-    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
-      const int n2 = cnt >> 1;
-      for (int i = threadIdx.x; i < n2; i += blockDim.x)
-        reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(src)[i];
-      if ((cnt & 1) && threadIdx.x == 0) dst[cnt - 1] = src[cnt - 1];
-    } else {
-      for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
+    const int U = m.send_off[W];
+    const uint32_t lmask = (F.lbits >= 32) ? 0xFFFFFFFFu : ((1u << F.lbits) - 1u);
+    const int i0 = (unit - s_begin[f]) * kIdChunk;
+#pragma unroll
+    for (int j = 0; j < kIdChunk / kShThreads; ++j) {
+      const int i = i0 + j * kShThreads + (int)threadIdx.x;
+      if (i >= U) break;
+      const uint32_t key = F.ukey[i];
+      int r = 0;
+      while (r + 1 < W && m.send_off[r + 1] <= i) ++r;
+      const int dst = m.remote_base[r] + (i - m.send_off[r]);
+      if (dst < F.cap)
+        reinterpret_cast<uint32_t*>(win(P, r) + F.ids_in_off)[dst] = key & lmask;
     }
   }
   signal_all_peers(P, 1, 2);
@@ -211,180 +265,76 @@ __global__ void __launch_bounds__(256) sh_push_ids_kernel(const __grid_constant_
 // ---- owner gather fused with the row push ---------------------------------------------
 constexpr int kShRowsPerGroup = 4;
 
-template <int V>
-__global__ void __launch_bounds__(256) sh_owner_gather_kernel(const __grid_constant__ ShParams P) {
-  wait_all_peers(P, 1);
+__global__ void __launch_bounds__(kShThreads) sh_owner_gather_kernel(const __grid_constant__ ShParams P) {
+  __shared__ int s_begin[kShMaxFeats + 1];
+  const bool arrived = wait_all_peers(P, 1);
+  int units = 0;
+  if ((int)threadIdx.x < P.n && arrived) {
+    const int per = (kShThreads >> P.feats[threadIdx.x].log2g) * kShRowsPerGroup;
+    units = (P.meta[threadIdx.x].recv_clamped + per - 1) / per;
+  }
+  const int total = sh_seg_scan(P.n, units, s_begin);
   bool oob = false;
-  // persistent CTAs: chunk -> (feature, first received position)
-  for (int chunk_id = blockIdx.x; chunk_id < P.total_ctas; chunk_id += gridDim.x) {
-    int lo = 0, hi = P.n - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (P.f[mid].cta_begin <= chunk_id) lo = mid; else hi = mid - 1;
-    }
-    const ShFeat& F = P.f[lo];
-    const ShFeatMeta& m = P.meta[lo];
+  for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    const int f = sh_seg_find(s_begin, P.n, unit);
+    const ShFeat& F = P.feats[f];
+    const ShFeatMeta& m = P.meta[f];
     const int log2g = F.log2g;
-    const int groups = 256 >> log2g;
+    const int G = 1 << log2g;
+    const int groups = kShThreads >> log2g;
     const int g = threadIdx.x >> log2g;
-    const int l = threadIdx.x & ((1 << log2g) - 1);
+    const int l = threadIdx.x & (G - 1);
     const int dim = F.dim;
-    const int p0 = (chunk_id - F.cta_begin) * groups * kShRowsPerGroup;
-    const int total = m.recv_clamped;
-    if (p0 >= total) continue;
-    const int64_t* ids_in = reinterpret_cast<const int64_t*>(win(P, P.me) + F.ids_in_off[P.parity]);
-    int col[V];
-    bool act[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      col[v] = ((v << log2g) + l) * 4;
-      act[v] = col[v] < dim;
-    }
-    int64_t row[kShRowsPerGroup];
-    int q[kShRowsPerGroup];
-    int dstrow[kShRowsPerGroup];
-    bool ok[kShRowsPerGroup];
-    int64_t idv[kShRowsPerGroup];
+    const int p0 = (unit - s_begin[f]) * groups * kShRowsPerGroup;
+    const int cnt = m.recv_clamped;
+    const uint32_t* ids_in = reinterpret_cast<const uint32_t*>(win(P, P.me) + F.ids_in_off);
+    uint32_t idv[kShRowsPerGroup];
 #pragma unroll
     for (int u = 0; u < kShRowsPerGroup; ++u) {  // all id loads in flight together
       const int p = p0 + u * groups + g;
-      idv[u] = ids_in[p < total ? p : p0];
+      idv[u] = ids_in[p < cnt ? p : p0];
     }
+    int64_t row[kShRowsPerGroup];
+    float* dst[kShRowsPerGroup];
 #pragma unroll
     for (int u = 0; u < kShRowsPerGroup; ++u) {
       const int p = p0 + u * groups + g;
-      ok[u] = p < total;
-      row[u] = -1; q[u] = 0; dstrow[u] = 0;
-      if (ok[u]) {
-        const int64_t id = idv[u];
-        int64_t r = -1;
-        if (id >= 0) r = P.div_shift >= 0 ? (int64_t)((uint64_t)id >> P.div_shift) : id / P.world;
-        if ((uint64_t)r >= (uint64_t)F.shard_rows) { oob = true; r = -1; }
-        row[u] = r;
-        int qq = 0;
-        while (qq + 1 < P.world && m.recv_base[qq + 1] <= p) ++qq;
-        q[u] = qq;
-        dstrow[u] = m.src_bucket_off[qq] + (p - m.recv_base[qq]);
+      row[u] = -1;
+      dst[u] = nullptr;
+      if (p < cnt) {
+        int q = 0;
+        while (q + 1 < P.world && m.recv_base[q + 1] <= p) ++q;
+        dst[u] = reinterpret_cast<float*>(win(P, q) + F.rows_in_off) +
+                 (int64_t)(m.src_bucket_off[q] + (p - m.recv_base[q])) * dim;
+        if ((int64_t)idv[u] < F.shard_rows) row[u] = (int64_t)idv[u];
+        else oob = true;  // the requester still gets a (zero) row
       }
     }
-    float4 val[kShRowsPerGroup][V];
+    // 16-byte column c of lane l: (l + k * G) * 4 floats, k = 0 .. ; dim <= 128 is one step
+    for (int c = l * 4; c < dim; c += G * 4) {
+      float4 val[kShRowsPerGroup];
 #pragma unroll
-    for (int u = 0; u < kShRowsPerGroup; ++u)
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok[u] && row[u] >= 0 && act[v])
-          val[u][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.shard + row[u] * dim + col[v]));
+      for (int u = 0; u < kShRowsPerGroup; ++u) {
+        val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row[u] >= 0) val[u] = ld_nc_f4(reinterpret_cast<const float4*>(F.shard + row[u] * dim + c));
       }
 #pragma unroll
-    for (int u = 0; u < kShRowsPerGroup; ++u) {
-      if (!ok[u]) continue;
-      float* dst = reinterpret_cast<float*>(win(P, q[u]) + F.rows_in_off) + (int64_t)dstrow[u] * dim;
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (act[v]) *reinterpret_cast<float4*>(dst + col[v]) = val[u][v];
+      for (int u = 0; u < kShRowsPerGroup; ++u)
+        if (dst[u] != nullptr) *reinterpret_cast<float4*>(dst[u] + c) = val[u];
     }
   }
   if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
   signal_all_peers(P, 2, 3);
 }
 
-// ---- backward: push row gradients to the owners ----------------------------------------
-template <int V>
-__global__ void __launch_bounds__(256) sh_push_grads_kernel(const __grid_constant__ ShParams P) {
-  for (int chunk_id = blockIdx.x; chunk_id < P.total_ctas; chunk_id += gridDim.x) {
-    int lo = 0, hi = P.n - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (P.f[mid].cta_begin <= chunk_id) lo = mid; else hi = mid - 1;
-    }
-    const ShFeat& F = P.f[lo];
-    const ShFeatMeta& m = P.meta[lo];
-    const int log2g = F.log2g;
-    const int groups = 256 >> log2g;
-    const int g = threadIdx.x >> log2g;
-    const int l = threadIdx.x & ((1 << log2g) - 1);
-    const int dim = F.dim;
-    const int p0 = (chunk_id - F.cta_begin) * groups * kShRowsPerGroup;
-    if (p0 >= F.nnz) continue;
-    const bool scaled = F.offsets != nullptr && F.combiner != HB_SUM;
-    int col[V];
-    bool act[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      col[v] = ((v << log2g) + l) * 4;
-      act[v] = col[v] < dim;
-    }
-    int bag[kShRowsPerGroup], r[kShRowsPerGroup], drow[kShRowsPerGroup];
-    float sc[kShRowsPerGroup];
-    bool ok[kShRowsPerGroup];
-    int jv[kShRowsPerGroup];
-#pragma unroll
-    for (int u = 0; u < kShRowsPerGroup; ++u) {  // independent loads first
-      const int p = p0 + u * groups + g;
-      const int pp = p < F.nnz ? p : p0;
-      jv[u] = F.part_idx[pp];
-      bag[u] = F.offsets != nullptr ? F.bag_of_pos[pp] : pp;
-    }
-#pragma unroll
-    for (int u = 0; u < kShRowsPerGroup; ++u) {
-      const int p = p0 + u * groups + g;
-      ok[u] = p < F.nnz;
-      r[u] = 0; drow[u] = 0; sc[u] = 1.0f;
-      if (ok[u]) {
-        if (scaled) {
-          const int64_t c = F.offsets[bag[u] + 1] - F.offsets[bag[u]];
-          sc[u] = (F.combiner == HB_MEAN) ? (float)c : __fsqrt_rn((float)c);
-        }
-        const int j = jv[u];
-        int rr = 0;
-        while (rr + 1 < P.world && m.send_off[rr + 1] <= j) ++rr;
-        r[u] = rr;
-        drow[u] = m.remote_base[rr] + (j - m.send_off[rr]);
-        if (drow[u] >= F.cap) ok[u] = false;  // overflow already flagged by the exchange
-      }
-    }
-    float4 val[kShRowsPerGroup][V];
-#pragma unroll
-    for (int u = 0; u < kShRowsPerGroup; ++u)
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok[u] && act[v])
-          val[u][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.grad + (int64_t)bag[u] * F.grad_stride + col[v]));
-      }
-#pragma unroll
-    for (int u = 0; u < kShRowsPerGroup; ++u) {
-      if (!ok[u]) continue;
-      float* dst = reinterpret_cast<float*>(win(P, r[u]) + F.grads_in_off) + (int64_t)drow[u] * dim;
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (act[v]) {
-          float4 x = val[u][v];
-          if (scaled)
-            x = make_float4(__fdiv_rn(x.x, sc[u]), __fdiv_rn(x.y, sc[u]), __fdiv_rn(x.z, sc[u]),
-                            __fdiv_rn(x.w, sc[u]));
-          *reinterpret_cast<float4*>(dst + col[v]) = x;
-        }
-    }
+// ---- backward: the gradient sums are in the owners' windows -> raise the flag ----------
+__global__ void __launch_bounds__(32) sh_signal_kernel(const __grid_constant__ ShParams P, int phase) {
+  // launched behind the emit kernels on the same stream: their peer stores are
+  // complete; one system fence, then the release stores
+  if ((int)threadIdx.x < P.world) {
+    __threadfence_system();
+    st_release_sys_u32(&ctl(P, threadIdx.x)->plan_flags[phase][P.me], P.epoch);
   }
-  signal_all_peers(P, 3, 4);
-}
-
-// bag index of every id position (CSR features), thread per bag
-__global__ void __launch_bounds__(256) sh_bag_map_kernel(const __grid_constant__ ShParams P) {
-  int lo = 0, hi = P.n - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (P.f[mid].cta_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-  }
-  const ShFeat& F = P.f[lo];
-  if (F.offsets == nullptr || F.bag_of_pos == nullptr) return;
-  const int b = (blockIdx.x - F.cta_begin) * 256 + threadIdx.x;
-  if (b >= F.nbags) return;
-  const int64_t s = F.offsets[b], e = F.offsets[b + 1];
-  if (s < 0 || e < s || e > F.nnz) { raise_status(P.status, HB_STATUS_BAD_OFFSETS); return; }
-  for (int64_t p = s; p < e; ++p) F.bag_of_pos[p] = b;
 }
 
 static int ilog2c32(int64_t x) {
@@ -393,17 +343,13 @@ static int ilog2c32(int64_t x) {
   return l;
 }
 
-static void sh_shape(int dim, int* log2g, int* v) {
+static void sh_shape(int dim, int* log2g) {
   const int vecs = dim / 4;
-  if (vecs <= 32) { *log2g = ilog2c32(vecs); *v = 1; return; }
-  *log2g = 5;
-  int vv = (vecs + 31) / 32, p = 1;
-  while (p < vv) p <<= 1;
-  *v = p;
+  *log2g = vecs <= 32 ? ilog2c32(vecs) : 5;
 }
 
 struct WindowLayout {
-  std::vector<uint64_t> ids_in[2], rows_in, grads_in;
+  std::vector<uint64_t> ids_in, rows_in, grads_in;
   std::vector<int64_t> cap;
   uint64_t total;
 };
@@ -421,10 +367,8 @@ static WindowLayout sh_window_layout(int world, int n, const int64_t* max_nnz, c
     if (cap < 1) cap = 1;
     L.cap[k] = cap;
   }
-  for (int par = 0; par < 2; ++par) {
-    L.ids_in[par].resize(n);
-    for (int k = 0; k < n; ++k) { L.ids_in[par][k] = o; o = align_up(o + (uint64_t)L.cap[k] * 8, 256); }
-  }
+  L.ids_in.resize(n);
+  for (int k = 0; k < n; ++k) { L.ids_in[k] = o; o = align_up(o + (uint64_t)L.cap[k] * 4, 256); }
   L.rows_in.resize(n);
   for (int k = 0; k < n; ++k) { L.rows_in[k] = o; o = align_up(o + (uint64_t)max_nnz[k] * dims[k] * 4, 256); }
   L.grads_in.resize(n);
@@ -445,62 +389,20 @@ struct hbShardedPlan {
   // local buffers (one allocation)
   unsigned char* local;
   size_t local_bytes;
-  std::vector<int64_t*> part_ids;
-  std::vector<int32_t*> part_idx, sizes, bag_of_pos;
+  std::vector<int32_t*> inv;
+  int32_t* owner_start1;   // [n][kMaxWorld], zeroed per step
+  hb::ShFeat* d_feats;
   hb::ShFeatMeta* meta;
-  void* part_ws;
-  size_t part_ws_bytes;
-  void* upd_ws;
-  size_t upd_ws_bytes;
-  uint32_t step;
+  void* req_ws;            // requester: sort / runs workspace (kept from forward to backward)
+  size_t req_ws_bytes;
+  void* own_ws;            // owner: sort / runs / apply workspace
+  size_t own_ws_bytes;
+  std::vector<hb::UpdViews> req_views;
+  uint32_t epoch;          // epoch of the last forward
   bool have_forward;
 };
 
 namespace hb {
-
-static int fill_params(const hbShardedPlan* pl, const hbShardedFeature* feats, int c0, int nc,
-                       ShParams* P, int32_t* d_status) {
-  const hbComm* c = pl->comm;
-  P->meta = pl->meta + c0;
-  P->peers = peer_ptrs(c);
-  P->window_off = control_bytes();
-  P->status = d_status;
-  P->n = nc;
-  P->me = c->rank;
-  P->world = c->world;
-  P->parity = pl->step & 1;
-  P->epoch = pl->step;
-  P->total_ctas = 0;
-  P->div_shift = ((c->world & (c->world - 1)) == 0) ? ilog2c32(c->world) : -1;
-  for (int j = 0; j < nc; ++j) {
-    const int k = c0 + j;
-    ShFeat& F = P->f[j];
-    const hbShardedFeature& f = feats[k];
-    int v;
-    F.part_ids = pl->part_ids[k];
-    F.part_idx = pl->part_idx[k];
-    F.sizes = pl->sizes[k];
-    F.bag_of_pos = pl->bag_of_pos[k];
-    F.ids_in_off[0] = pl->layout.ids_in[0][k];
-    F.ids_in_off[1] = pl->layout.ids_in[1][k];
-    F.rows_in_off = pl->layout.rows_in[k];
-    F.grads_in_off = pl->layout.grads_in[k];
-    F.cap = (int32_t)pl->layout.cap[k];
-    F.dim = pl->dims[k];
-    sh_shape(F.dim, &F.log2g, &v);
-    F.max_nnz = (int32_t)pl->max_nnz[k];
-    F.shard = f.shard;
-    F.grad = f.grad;
-    F.offsets = f.offsets;
-    F.shard_rows = f.shard_rows;
-    F.grad_stride = f.grad_stride;
-    F.nnz = (int32_t)f.nnz;
-    F.nbags = (int32_t)f.nbags;
-    F.combiner = f.combiner;
-    F.cta_begin = 0;
-  }
-  return HB_OK;
-}
 
 static int validate_sharded(const hbShardedPlan* pl, const hbShardedFeature* feats, bool backward) {
   for (int k = 0; k < pl->n; ++k) {
@@ -510,7 +412,7 @@ static int validate_sharded(const hbShardedPlan* pl, const hbShardedFeature* fea
                (long long)f.nnz, (long long)pl->max_nnz[k]);
     HB_REQUIRE(f.nbags >= 0 && f.nbags <= INT32_MAX, "sharded: feature %d bad nbags", k);
     HB_REQUIRE(f.offsets != nullptr || f.nnz == f.nbags, "sharded: feature %d has no offsets, so nnz must equal nbags", k);
-    HB_REQUIRE(f.shard_rows >= 0 && f.shard_rows < ((int64_t)1 << 32) - 2, "sharded: feature %d bad shard_rows", k);
+    HB_REQUIRE(f.shard_rows >= 0 && f.shard_rows < ((int64_t)1 << 31) / pl->comm->world, "sharded: feature %d bad shard_rows", k);
     HB_REQUIRE(f.combiner >= HB_SUM && f.combiner <= HB_SQRTN, "sharded: feature %d bad combiner", k);
     HB_REQUIRE(f.shard != nullptr || f.shard_rows == 0, "sharded: feature %d null shard", k);
     HB_REQUIRE(f.ids != nullptr || f.nnz == 0, "sharded: feature %d null ids", k);
@@ -523,6 +425,52 @@ static int validate_sharded(const hbShardedPlan* pl, const hbShardedFeature* fea
     }
   }
   return HB_OK;
+}
+
+static void requester_jobs(const hbShardedPlan* pl, const hbShardedFeature* feats, bool backward,
+                           std::vector<hbUpdateFeature>* uf, std::vector<UpdExtra>* ex) {
+  const int n = pl->n, W = pl->comm->world;
+  uf->resize(n);
+  ex->resize(n);
+  for (int k = 0; k < n; ++k) {
+    hbUpdateFeature& u = (*uf)[k];
+    memset(&u, 0, sizeof(u));
+    // any owner's shard has at most my rows + 1 (embedding/variables.py:107-109)
+    u.rows = feats[k].shard_rows + 1;
+    u.ids = feats[k].ids;
+    u.offsets = feats[k].offsets;
+    u.nbags = feats[k].nbags;
+    u.nnz = feats[k].nnz;
+    u.grad = backward ? feats[k].grad : nullptr;
+    u.grad_stride = backward ? feats[k].grad_stride : feats[k].dim;
+    u.dim = feats[k].dim;
+    u.combiner = feats[k].combiner;
+    u.id_div = W;
+    UpdExtra& e = (*ex)[k];
+    e.key_kind = 1;
+    e.lbits = ilog2c32(u.rows + 1);
+    e.inv = pl->inv[k];
+    e.owner_start1 = pl->owner_start1 + (size_t)k * kMaxWorld;
+    e.emit_send_off = pl->meta[k].send_off;
+    e.emit_remote_base = pl->meta[k].remote_base;
+    e.emit_off = pl->layout.grads_in[k];
+    e.emit_cap = (int32_t)pl->layout.cap[k];
+  }
+}
+
+static ShParams sh_params(const hbShardedPlan* pl, int32_t* d_status) {
+  const hbComm* c = pl->comm;
+  ShParams P;
+  P.feats = pl->d_feats;
+  P.meta = pl->meta;
+  P.peers = peer_ptrs(c);
+  P.window_off = control_bytes();
+  P.status = d_status;
+  P.n = pl->n;
+  P.me = c->rank;
+  P.world = c->world;
+  P.epoch = pl->epoch;
+  return P;
 }
 
 }  // namespace hb
@@ -545,74 +493,68 @@ int hbShardedPlanCreate(hbComm* comm, int n, const int64_t* max_nnz, const int32
   HB_REQUIRE(comm->reserved_bytes == 0, "hbShardedPlanCreate: this communicator already hosts a plan");
   if (capacity_factor < 1.0) capacity_factor = 1.0;
   for (int k = 0; k < n; ++k) {
-    HB_REQUIRE(max_nnz[k] >= 1 && max_nnz[k] <= INT32_MAX / 2, "hbShardedPlanCreate: bad max_nnz[%d]", k);
+    HB_REQUIRE(max_nnz[k] >= 1 && max_nnz[k] <= INT32_MAX / 4, "hbShardedPlanCreate: bad max_nnz[%d]", k);
     HB_REQUIRE(dims[k] >= 4 && dims[k] % 4 == 0 && dims[k] <= 1024, "hbShardedPlanCreate: dim[%d]=%d must be a multiple of 4 in [4,1024]", k, dims[k]);
   }
+  WindowLayout layout = sh_window_layout(comm->world, n, max_nnz, dims, capacity_factor);
+  for (int k = 0; k < n; ++k)
+    HB_REQUIRE(layout.cap[k] <= INT32_MAX / 4, "hbShardedPlanCreate: capacity of feature %d too large", k);
+  if (layout.total > comm->window_bytes) {
+    set_last_error("hbShardedPlanCreate: window %zu B < %llu B needed (see hbShardedPlanWindowBytes)",
+                   comm->window_bytes, (unsigned long long)layout.total);
+    return HB_ERR_WORKSPACE;
+  }
+  // workspaces: requester (max_nnz entries, bags possible) and owner (cap entries)
+  static const int64_t kDummy = 0;
+  std::vector<hbUpdateFeature> rq(n), ow(n);
+  for (int k = 0; k < n; ++k) {
+    memset(&rq[k], 0, sizeof(hbUpdateFeature));
+    rq[k].nnz = rq[k].nbags = max_nnz[k];
+    rq[k].offsets = &kDummy;  // size for the CSR form
+    rq[k].dim = dims[k];
+    ow[k] = rq[k];
+    ow[k].offsets = nullptr;
+    ow[k].nnz = ow[k].nbags = layout.cap[k];
+  }
+  const size_t req_ws = sparse_update_workspace_bytes(n, rq.data());
+  const size_t own_ws = sparse_update_workspace_bytes(n, ow.data());
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  std::vector<size_t> o_inv(n);
+  for (int k = 0; k < n; ++k) o_inv[k] = take((size_t)max_nnz[k] * 4);
+  const size_t o_start = take((size_t)n * kMaxWorld * 4);
+  const size_t o_feats = take(sizeof(ShFeat) * n);
+  const size_t o_meta = take(sizeof(ShFeatMeta) * n);
+  const size_t o_rws = take(req_ws);
+  const size_t o_ows = take(own_ws);
   hbShardedPlan* pl = new hbShardedPlan();
   pl->comm = comm;
   pl->n = n;
   pl->cf = capacity_factor;
   pl->max_nnz.assign(max_nnz, max_nnz + n);
   pl->dims.assign(dims, dims + n);
-  pl->layout = sh_window_layout(comm->world, n, max_nnz, dims, capacity_factor);
-  for (int k = 0; k < n; ++k)
-    HB_REQUIRE(pl->layout.cap[k] <= INT32_MAX / 2, "hbShardedPlanCreate: capacity of feature %d too large", k);
-  if (pl->layout.total > comm->window_bytes) {
-    set_last_error("hbShardedPlanCreate: window %zu B < %llu B needed (see hbShardedPlanWindowBytes)",
-                   comm->window_bytes, (unsigned long long)pl->layout.total);
-    delete pl;
-    return HB_ERR_WORKSPACE;
-  }
-  // local buffers
-  std::vector<int32_t> lens(n);
-  for (int k = 0; k < n; ++k) lens[k] = (int32_t)max_nnz[k];
-  size_t part_ws = 0;
-  int rc = hbPartitionWorkspaceBytes(n, lens.data(), comm->world, &part_ws);
-  if (rc != HB_OK) { delete pl; return rc; }
-  std::vector<hbUpdateFeature> uf(n);
-  for (int k = 0; k < n; ++k) {
-    memset(&uf[k], 0, sizeof(hbUpdateFeature));
-    uf[k].rows = ((int64_t)1 << 32) - 3;  // worst case number of radix passes
-    uf[k].nnz = uf[k].nbags = pl->layout.cap[k];
-    uf[k].dim = dims[k];
-    uf[k].id_div = comm->world;
-  }
-  size_t upd_ws = 0;
-  rc = hbGroupSparseUpdateWorkspaceBytes(n, uf.data(), &upd_ws);
-  if (rc != HB_OK) { delete pl; return rc; }
-  size_t o = 0;
-  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-  std::vector<size_t> o_ids(n), o_idx(n), o_sizes(n), o_bag(n);
-  for (int k = 0; k < n; ++k) {
-    o_ids[k] = take((size_t)max_nnz[k] * 8);
-    o_idx[k] = take((size_t)max_nnz[k] * 4);
-    o_sizes[k] = take((size_t)kMaxWorld * 4);
-    o_bag[k] = take((size_t)max_nnz[k] * 4);
-  }
-  const size_t o_meta = take(sizeof(ShFeatMeta) * n);
-  const size_t o_pws = take(part_ws);
-  const size_t o_uws = take(upd_ws);
+  pl->layout = layout;
   pl->local_bytes = o;
+  pl->local = nullptr;
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&pl->local), pl->local_bytes);
+  if (e == cudaSuccess) e = cudaMemset(pl->local, 0, pl->local_bytes);
   if (e != cudaSuccess) {
     set_last_error("hbShardedPlanCreate: cudaMalloc(%zu) failed: %s", pl->local_bytes, cudaGetErrorString(e));
+    if (pl->local) cudaFree(pl->local);
     delete pl;
     return HB_ERR_CUDA;
   }
-  cudaMemset(pl->local, 0, pl->local_bytes);
-  pl->part_ids.resize(n); pl->part_idx.resize(n); pl->sizes.resize(n); pl->bag_of_pos.resize(n);
-  for (int k = 0; k < n; ++k) {
-    pl->part_ids[k] = reinterpret_cast<int64_t*>(pl->local + o_ids[k]);
-    pl->part_idx[k] = reinterpret_cast<int32_t*>(pl->local + o_idx[k]);
-    pl->sizes[k] = reinterpret_cast<int32_t*>(pl->local + o_sizes[k]);
-    pl->bag_of_pos[k] = reinterpret_cast<int32_t*>(pl->local + o_bag[k]);
-  }
+  pl->inv.resize(n);
+  for (int k = 0; k < n; ++k) pl->inv[k] = reinterpret_cast<int32_t*>(pl->local + o_inv[k]);
+  pl->owner_start1 = reinterpret_cast<int32_t*>(pl->local + o_start);
+  pl->d_feats = reinterpret_cast<ShFeat*>(pl->local + o_feats);
   pl->meta = reinterpret_cast<ShFeatMeta*>(pl->local + o_meta);
-  pl->part_ws = pl->local + o_pws;
-  pl->part_ws_bytes = part_ws;
-  pl->upd_ws = pl->local + o_uws;
-  pl->upd_ws_bytes = upd_ws;
-  pl->step = 0;
+  pl->req_ws = pl->local + o_rws;
+  pl->req_ws_bytes = req_ws;
+  pl->own_ws = pl->local + o_ows;
+  pl->own_ws_bytes = own_ws;
+  pl->req_views.resize(n);
+  pl->epoch = 0;
   pl->have_forward = false;
   comm->reserved_bytes = align_up(pl->layout.total, 4096);
   cudaDeviceSynchronize();
@@ -638,83 +580,78 @@ int hbShardedLookupForward(hbShardedPlan* pl, const hbShardedFeature* feats, int
   if (rc != HB_OK) return rc;
   hbComm* c = pl->comm;
   const int n = pl->n, W = c->world;
-  pl->step++;
+  // the epoch lives in the communicator: flags left behind by an earlier plan on the
+  // same communicator can never satisfy a wait of this one
+  pl->epoch = ++c->plan_epoch;
   pl->have_forward = true;
+  std::vector<hbUpdateFeature> uf;
+  std::vector<UpdExtra> ex;
+  requester_jobs(pl, feats, false, &uf, &ex);
+  const int sms = device_sm_count();
 
-  // K1: stable partition of every feature's ids by id % W
-  {
-    std::vector<const void*> in(n);
-    std::vector<void*> out(n);
-    std::vector<int32_t*> sz(n), ix(n);
-    std::vector<int32_t> lens(n);
-    for (int k = 0; k < n; ++k) {
-      in[k] = feats[k].ids; out[k] = pl->part_ids[k]; sz[k] = pl->sizes[k]; ix[k] = pl->part_idx[k];
-      lens[k] = (int32_t)feats[k].nnz;
+  return comm_submit(c, kOpShardedFwd, 4, stream, [&](int phase) -> int {
+    int rc2 = HB_OK;
+    if (phase == 0) {
+      // requester: sort by (owner, local row), find the unique ids, publish the counts
+      HB_CUDA_OK(cudaMemsetAsync(pl->owner_start1, 0, (size_t)n * kMaxWorld * 4, stream));
+      rc2 = sparse_update_run(n, uf.data(), nullptr, pl->req_ws, pl->req_ws_bytes, d_status, stream,
+                              nullptr, ex.data(), nullptr, kPhaseSort, pl->req_views.data());
+      if (rc2 != HB_OK) return rc2;
+      std::vector<ShFeat> hf(n);
+      for (int k = 0; k < n; ++k) {
+        ShFeat& F = hf[k];
+        F.ukey = pl->req_views[k].ukey;
+        F.counts = pl->req_views[k].counts;
+        F.owner_start1 = pl->owner_start1 + (size_t)k * kMaxWorld;
+        F.shard = feats[k].shard;
+        F.shard_rows = feats[k].shard_rows;
+        F.ids_in_off = pl->layout.ids_in[k];
+        F.rows_in_off = pl->layout.rows_in[k];
+        F.grads_in_off = pl->layout.grads_in[k];
+        F.cap = (int32_t)pl->layout.cap[k];
+        F.dim = pl->dims[k];
+        sh_shape(F.dim, &F.log2g);
+        F.lbits = ex[k].lbits;
+        F.max_nnz = (int32_t)pl->max_nnz[k];
+        F.pad = 0;
+      }
+      // pageable source: staged by the driver before the call returns
+      HB_CUDA_OK(cudaMemcpyAsync(pl->d_feats, hf.data(), sizeof(ShFeat) * n, cudaMemcpyHostToDevice, stream));
+      ShParams P = sh_params(pl, d_status);
+      KernelScope ks(HB_K_SH_PUBLISH, stream);
+      sh_publish_kernel<<<1, kShThreads, 0, stream>>>(P);
+      HB_CUDA_OK(cudaGetLastError());
+      return HB_OK;
     }
-    rc = hbPartitionByModuloN(HB_I64, n, in.data(), lens.data(), W, out.data(), sz.data(), ix.data(),
-                              pl->part_ws, pl->part_ws_bytes, stream_);
-    if (rc != HB_OK) return rc;
-  }
-  HB_REQUIRE(n <= kShMaxFeats, "hbShardedLookupForward: more than %d sharded features per plan", kShMaxFeats);
-  ShParams P;
-  fill_params(pl, feats, 0, n, &P, d_status);
-  // exchange
-  {
-    KernelScope ks(HB_K_SH_EXCHANGE, stream);
-    sh_exchange_kernel<<<1, 256, 0, stream>>>(P);
-  }
-  HB_CUDA_OK(cudaGetLastError());
-  // push ids
-  {
-    int items = 0;
-    for (int k = 0; k < n; ++k) items += W * (int)((pl->max_nnz[k] + kIdChunk - 1) / kIdChunk);
-    ShParams Q = P;
-    Q.total_ctas = items;
-    const int maxg = device_sm_count() * 4;
-    KernelScope ks(HB_K_SH_PUSH_IDS, stream);
-    sh_push_ids_kernel<<<items < maxg ? items : maxg, 256, 0, stream>>>(Q);
-  }
-  HB_CUDA_OK(cudaGetLastError());
-  // owner gather + row push, one launch per V
-  for (int V = 1; V <= 8; V <<= 1) {
-    ShParams Q = P;
-    int m = 0, ctas = 0;
-    std::vector<int> idx;
-    for (int k = 0; k < n; ++k) {
-      int l2, v;
-      sh_shape(pl->dims[k], &l2, &v);
-      if (v != V) continue;
-      Q.f[m] = P.f[k];
-      Q.f[m].cta_begin = ctas;
-      const int per = (256 >> l2) * kShRowsPerGroup;
-      ctas += (int)((pl->layout.cap[k] + per - 1) / per);
-      idx.push_back(k);
-      ++m;
+    ShParams P = sh_params(pl, d_status);
+    if (phase == 1) {
+      {
+        KernelScope ks(HB_K_SH_EXCHANGE, stream);
+        sh_meta_kernel<<<1, kShThreads, 0, stream>>>(P);
+      }
+      HB_CUDA_OK(cudaGetLastError());
+      int64_t units = 0;
+      for (int k = 0; k < n; ++k) units += (feats[k].nnz + kIdChunk - 1) / kIdChunk;
+      const int maxg = sms * 4;
+      const int grid = units < 1 ? 1 : (units < maxg ? (int)units : maxg);
+      KernelScope ks(HB_K_SH_PUSH_IDS, stream);
+      sh_push_ids_kernel<<<grid, kShThreads, 0, stream>>>(P);
+      HB_CUDA_OK(cudaGetLastError());
+      return HB_OK;
     }
-    if (m == 0) continue;
-    // meta must follow the compaction: use a per-V meta view only when contiguous
-    HB_REQUIRE(m == n, "hbShardedLookupForward: all sharded features of a plan must share dim <= 128 or the same V");
-    Q.n = m;
-    Q.total_ctas = ctas;
-    const int maxg = device_sm_count() * 8;
-    const int grid = ctas < maxg ? ctas : maxg;
-    KernelScope ks(HB_K_SH_OWNER_GATHER, stream);
-    switch (V) {
-      case 1: sh_owner_gather_kernel<1><<<grid, 256, 0, stream>>>(Q); break;
-      case 2: sh_owner_gather_kernel<2><<<grid, 256, 0, stream>>>(Q); break;
-      case 4: sh_owner_gather_kernel<4><<<grid, 256, 0, stream>>>(Q); break;
-      default: sh_owner_gather_kernel<8><<<grid, 256, 0, stream>>>(Q); break;
+    if (phase == 2) {
+      KernelScope ks(HB_K_SH_OWNER_GATHER, stream);
+      sh_owner_gather_kernel<<<sms * 8, kShThreads, 0, stream>>>(P);
+      HB_CUDA_OK(cudaGetLastError());
+      return HB_OK;
     }
-  }
-  HB_CUDA_OK(cudaGetLastError());
-  // stitch + pool from the local rows_in window
-  {
+    // stitch + pool from the local rows_in window through the inverse map
     std::vector<hbLookupFeature> lf(n);
     std::vector<const int32_t*> idx32(n);
     unsigned char* mywin = c->base + control_bytes();
     for (int k = 0; k < n; ++k) {
       lf[k].table = reinterpret_cast<const float*>(mywin + pl->layout.rows_in[k]);
-      lf[k].rows = feats[k].nnz;
+      lf[k].rows = pl->max_nnz[k];
       lf[k].ids = nullptr;
       lf[k].offsets = feats[k].offsets;
       lf[k].nbags = feats[k].nbags;
@@ -723,14 +660,13 @@ int hbShardedLookupForward(hbShardedPlan* pl, const hbShardedFeature* feats, int
       lf[k].dim = feats[k].dim;
       lf[k].combiner = feats[k].combiner;
       lf[k].id_div = 1;
-      idx32[k] = pl->part_idx[k];
+      lf[k].nnz = feats[k].nnz;
+      idx32[k] = pl->inv[k];
     }
     Control* mine = reinterpret_cast<Control*>(c->base);
-    WaitSpec w{&mine->plan_flags[2][0], pl->step, W};
-    rc = lookup_forward_run(n, lf.data(), idx32.data(), &w, true, d_status, stream, HB_K_SH_STITCH);
-    if (rc != HB_OK) return rc;
-  }
-  return HB_OK;
+    WaitSpec w{&mine->plan_flags[2][0], pl->epoch, W};
+    return lookup_forward_run(n, lf.data(), idx32.data(), &w, true, d_status, stream, HB_K_SH_STITCH);
+  });
 }
 
 int hbShardedLookupBackwardUpdate(hbShardedPlan* pl, const hbShardedFeature* feats,
@@ -744,79 +680,53 @@ int hbShardedLookupBackwardUpdate(hbShardedPlan* pl, const hbShardedFeature* fea
   hbComm* c = pl->comm;
   const int n = pl->n, W = c->world;
   pl->have_forward = false;
-  ShParams P;
-  fill_params(pl, feats, 0, n, &P, d_status);
-  // bag map for CSR features
-  {
-    ShParams Q = P;
-    int ctas = 0;
-    bool any = false;
-    for (int k = 0; k < n; ++k) {
-      Q.f[k].cta_begin = ctas;
-      ctas += (int)((feats[k].nbags + 255) / 256) + 1;
-      any = any || feats[k].offsets != nullptr;
-    }
-    if (any) {
-      KernelScope ks(HB_K_BAG_MAP, stream);
-      sh_bag_map_kernel<<<ctas, 256, 0, stream>>>(Q);
+  std::vector<hbUpdateFeature> uf;
+  std::vector<UpdExtra> ex;
+  requester_jobs(pl, feats, true, &uf, &ex);
+
+  return comm_submit(c, kOpShardedBwd, 2, stream, [&](int phase) -> int {
+    ShParams P = sh_params(pl, d_status);
+    if (phase == 0) {
+      // requester: per-unique gradient sums straight into the owners' windows
+      EmitCtx em;
+      em.peers = P.peers;
+      em.window_off = P.window_off;
+      em.world = W;
+      int rc2 = sparse_update_run(n, uf.data(), nullptr, pl->req_ws, pl->req_ws_bytes, d_status, stream,
+                                  nullptr, ex.data(), &em, kPhaseApply, nullptr);
+      if (rc2 != HB_OK) return rc2;
+      KernelScope ks(HB_K_SH_PUSH_GRADS, stream);
+      sh_signal_kernel<<<1, 32, 0, stream>>>(P, 3);
       HB_CUDA_OK(cudaGetLastError());
+      return HB_OK;
     }
-  }
-  // push row gradients to the owners
-  for (int V = 1; V <= 8; V <<= 1) {
-    ShParams Q = P;
-    int m = 0, ctas = 0;
-    for (int k = 0; k < n; ++k) {
-      int l2, v;
-      sh_shape(pl->dims[k], &l2, &v);
-      if (v != V) continue;
-      Q.f[m].cta_begin = ctas;
-      const int per = (256 >> l2) * kShRowsPerGroup;
-      ctas += (int)((pl->max_nnz[k] + per - 1) / per);
-      ++m;
-    }
-    if (m == 0) continue;
-    HB_REQUIRE(m == n, "hbShardedLookupBackwardUpdate: all sharded features of a plan must share V");
-    Q.total_ctas = ctas;
-    const int maxg = device_sm_count() * 8;
-    const int grid = ctas < maxg ? ctas : maxg;
-    KernelScope ks(HB_K_SH_PUSH_GRADS, stream);
-    switch (V) {
-      case 1: sh_push_grads_kernel<1><<<grid, 256, 0, stream>>>(Q); break;
-      case 2: sh_push_grads_kernel<2><<<grid, 256, 0, stream>>>(Q); break;
-      case 4: sh_push_grads_kernel<4><<<grid, 256, 0, stream>>>(Q); break;
-      default: sh_push_grads_kernel<8><<<grid, 256, 0, stream>>>(Q); break;
-    }
-  }
-  HB_CUDA_OK(cudaGetLastError());
-  // owner side: sort the received ids, sum duplicates, apply the optimizer
-  {
-    std::vector<hbUpdateFeature> uf(n);
+    // owner: sort the received rows, sum duplicates across ranks, apply the optimizer
+    std::vector<hbUpdateFeature> of(n);
+    std::vector<UpdExtra> oe(n);
     unsigned char* mywin = c->base + control_bytes();
-    const int par = pl->step & 1;
     for (int k = 0; k < n; ++k) {
-      uf[k].table = feats[k].shard;
-      uf[k].slot0 = feats[k].slot0;
-      uf[k].slot1 = feats[k].slot1;
-      uf[k].rows = feats[k].shard_rows;
-      uf[k].ids = reinterpret_cast<const int64_t*>(mywin + pl->layout.ids_in[par][k]);
-      uf[k].offsets = nullptr;
-      uf[k].nbags = uf[k].nnz = pl->layout.cap[k];
-      uf[k].grad = reinterpret_cast<const float*>(mywin + pl->layout.grads_in[k]);
-      uf[k].grad_stride = pl->dims[k];
-      uf[k].dim = pl->dims[k];
-      uf[k].combiner = HB_SUM;
-      uf[k].id_div = W;
+      memset(&of[k], 0, sizeof(hbUpdateFeature));
+      of[k].table = feats[k].shard;
+      of[k].slot0 = feats[k].slot0;
+      of[k].slot1 = feats[k].slot1;
+      of[k].rows = feats[k].shard_rows;
+      of[k].ids = nullptr;
+      of[k].offsets = nullptr;
+      of[k].nbags = of[k].nnz = pl->layout.cap[k];
+      of[k].grad = reinterpret_cast<const float*>(mywin + pl->layout.grads_in[k]);
+      of[k].grad_stride = pl->dims[k];
+      of[k].dim = pl->dims[k];
+      of[k].combiner = HB_SUM;
+      of[k].id_div = W;
+      oe[k].key_kind = 2;
+      oe[k].keys32 = reinterpret_cast<const uint32_t*>(mywin + pl->layout.ids_in[k]);
+      oe[k].n_dev = &pl->meta[k].recv_clamped;
     }
     Control* mine = reinterpret_cast<Control*>(c->base);
-    WaitSpec w{&mine->plan_flags[3][0], pl->step, W};
-    std::vector<const int32_t*> ndev(n);
-    for (int k = 0; k < n; ++k) ndev[k] = &pl->meta[k].recv_clamped;
-    rc = sparse_update_run(n, uf.data(), opt, pl->upd_ws, pl->upd_ws_bytes, d_status, stream, &w,
-                           ndev.data());
-    if (rc != HB_OK) return rc;
-  }
-  return HB_OK;
+    WaitSpec w{&mine->plan_flags[3][0], pl->epoch, W};
+    return sparse_update_run(n, of.data(), opt, pl->own_ws, pl->own_ws_bytes, d_status, stream, &w,
+                             oe.data(), nullptr, kPhaseSort | kPhaseApply, nullptr);
+  });
 }
 
 }  // extern "C"

@@ -3,30 +3,41 @@
 //
 // Pipeline (all features of the group per launch):
 //   1. bag_of_position : CSR features only -- bag index of every id position.
-//   2. LSD radix sort  : (local row, bag) pairs grouped by row, 9-bit digits,
-//                        stable, so entries of a row stay in position order
-//                        (bucket.cuh; 1..4 passes depending on the table size).
-//   3. update kernel   : a sub-warp group of G lanes walks a tile of C sorted
-//                        entries; gradient rows of a run (same row id) are summed
-//                        in registers in position order and the optimizer is
-//                        applied once per unique row (one read-modify-write of
-//                        the table row and its slot rows).  Runs that cross tile
-//                        borders are combined in shared memory inside the CTA
-//                        ("super-tile"), in tile order.
-//   4. fix-up kernel   : rows that span super-tiles (hot keys) are finished by
-//                        chaining the per-super-tile partial sums, in order.
-// Summation order is a fixed function of the input => bit-reproducible.
+//   2. LSD radix sort  : (row key, bag) pairs grouped by key, 9-bit digits, stable,
+//                        so entries of a row stay in position order (bucket.cuh).
+//   3. runs kernel     : one scan over the sorted keys -> unique keys, the first
+//                        entry of every run, the unique count (all on device).
+//   4. short kernel    : work item = one UNIQUE row.  A sub-warp group of G lanes
+//                        (G*4 floats = one row) loads the run bounds, sums the
+//                        gradient rows of the run in position order in registers and
+//                        applies the optimizer once (one read-modify-write of the
+//                        table row and its slot rows).  No cross-thread state, no
+//                        shuffles, no barriers.  Runs longer than kShortMax are
+//                        queued instead.
+//   5. long kernel     : hot rows.  A queued run is cut into pieces of kPiece
+//                        entries, one warp per piece: its groups sum interleaved
+//                        entries, the group sums are combined in a fixed shuffle
+//                        tree; multi-piece runs park piece sums in global memory
+//                        and the warp that arrives last adds them in piece order.
+// The order of every floating-point addition is a fixed function of the run length
+// => bit-reproducible (test_determinism), whatever the scheduling.
 //
-// Algorithmic HBM bytes per looked-up id without duplicates (Adagrad, fp32):
-//   8 (id) + 4*dim (grad) + 2*4*dim (w, acc read) + 2*4*dim (w, acc write).
+// Algorithmic HBM bytes (Adagrad, fp32): per looked-up id 8 (sorted key + bag) +
+// 4*dim (gradient row); per unique row 4*4*dim (table + accumulator, read + write).
+#include <math.h>
+
 #include "bucket.cuh"
+#include "update.cuh"
 
 namespace hb {
 
 constexpr int kUpdThreads = 256;
 constexpr int kMaxUpdFeats = 96;
+constexpr int kShortMax = 16;   // runs up to this many entries are summed by one group
+constexpr int kPiece = 256;     // entries per piece of a long run (one warp)
+constexpr int kNU = 2;          // unique rows in flight per group (short kernel)
 
-enum { kFirstOpen = 1, kBoth = 2, kLastOpen = 4 };
+enum { kModeApply = 0, kModeEmit = 1 };
 
 struct UpdFeat {
   float* table;
@@ -34,51 +45,68 @@ struct UpdFeat {
   float* slot1;
   const float* grad;
   const int64_t* offsets;   // bag sizes for mean/sqrtn (nullptr: one id per bag)
-  const uint32_t* keys;     // sorted local rows
-  const int32_t* bags;      // bag index of each sorted entry
-  float* st_part;           // [nst][2][dim] partial sums of open runs
-  uint32_t* st_key;         // [nst][2]
-  int32_t* st_flag;         // [nst]
-  const int32_t* n_dev;     // may be nullptr: device-side number of entries (<= n)
+  const uint32_t* ukey;     // [U] unique keys
+  const int32_t* ustart;    // [U+1]
+  const int32_t* counts;    // [0] = U
+  const int32_t* vals;      // bag index of each sorted entry (or its position, see pos2bag)
+  const int32_t* pos2bag;   // != nullptr: vals hold input positions, bag = pos2bag[position]
+  const int32_t* emit_send_off;
+  const int32_t* emit_remote_base;
+  uint64_t emit_off;
   int64_t rows;
   int64_t grad_stride;
-  int32_t n;
+  int32_t emit_cap;
   int32_t dim;
   int32_t combiner;
   int32_t log2g;
-  int32_t cta_begin;        // first super-tile (== CTA) of this feature
-  int32_t nst;              // number of super-tiles
+  int32_t max_chunks;       // static bound of the number of chunks of this feature
 };
+
+struct LongItem { int32_t feat, u, piece, pbase; };
 
 struct UpdParams {
   UpdFeat f[kMaxUpdFeats];
   WaitSpec wait;
+  EmitCtx emit;
   int32_t* status;
+  int32_t* long_count;      // [0] queued pieces, [1] reserved partial slots
+  LongItem* items;
+  float* part;              // [part_cap][part_stride] piece sums of multi-piece runs
+  int32_t* tickets;         // [part_cap] arrival counters, indexed by the run's pbase
+  int32_t item_cap, part_cap, part_stride;
   int32_t nfeats;
-  int32_t total_ctas;
   int32_t opt;
-  float lr;        // Adagrad/SGD: lr ; LazyAdam: bias-corrected lr_t
+  int32_t fast;             // approximate sqrt/div (MUFU) instead of the IEEE sequence
+  float lr;                 // Adagrad/SGD: lr ; LazyAdam: bias-corrected lr_t
   float beta1, beta2, eps;
   float omb1, omb2;
 };
-
-__device__ __forceinline__ int find_upd_feat(const UpdParams& P, int cta) {
-  int lo = 0, hi = P.nfeats - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (P.f[mid].cta_begin <= cta) lo = mid; else hi = mid - 1;
-  }
-  return lo;
-}
 
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float4 f4_add_rn(const float4& a, const float4& b) {
   return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z),
                      __fadd_rn(a.w, b.w));
 }
+__device__ __forceinline__ float4 f4_div_rn(const float4& a, float c) {
+  return make_float4(__fdiv_rn(a.x, c), __fdiv_rn(a.y, c), __fdiv_rn(a.z, c), __fdiv_rn(a.w, c));
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float4* p) {  // L2 only (data written by other SMs)
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
 
 // One optimizer step on 4 consecutive elements of a row (values in registers).
-template <int OPT>
+// FAST = false is the IEEE sequence of the oracle (bit-exact); FAST = true uses
+// the MUFU approximations (sqrt.approx / div.approx, <= 2 ulp each) -- the class of
+// arithmetic TF's GPU kernels use (rsqrt) -- selected by HB_OPT_FLAG_FAST_MATH.
+template <int OPT, bool FAST>
 __device__ __forceinline__ void opt_step4(const UpdParams& P, float4& wv, float4& s0v, float4& s1v,
                                           const float4& g) {
   const float gg[4] = {g.x, g.y, g.z, g.w};
@@ -89,7 +117,8 @@ __device__ __forceinline__ void opt_step4(const UpdParams& P, float4& wv, float4
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       aa[i] = __fadd_rn(aa[i], __fmul_rn(gg[i], gg[i]));
-      ww[i] = __fsub_rn(ww[i], __fdiv_rn(__fmul_rn(P.lr, gg[i]), __fsqrt_rn(aa[i])));
+      if constexpr (FAST) ww[i] = __fsub_rn(ww[i], __fdividef(__fmul_rn(P.lr, gg[i]), sqrt_approx(aa[i])));
+      else ww[i] = __fsub_rn(ww[i], __fdiv_rn(__fmul_rn(P.lr, gg[i]), __fsqrt_rn(aa[i])));
     }
     s0v = make_float4(aa[0], aa[1], aa[2], aa[3]);
   } else if constexpr (OPT == HB_OPT_LAZY_ADAM) {
@@ -100,8 +129,10 @@ __device__ __forceinline__ void opt_step4(const UpdParams& P, float4& wv, float4
     for (int i = 0; i < 4; ++i) {
       mm[i] = __fadd_rn(__fmul_rn(P.beta1, mm[i]), __fmul_rn(P.omb1, gg[i]));
       v2[i] = __fadd_rn(__fmul_rn(P.beta2, v2[i]), __fmul_rn(P.omb2, __fmul_rn(gg[i], gg[i])));
-      ww[i] = __fsub_rn(ww[i], __fdiv_rn(__fmul_rn(P.lr, mm[i]),
-                                         __fadd_rn(__fsqrt_rn(v2[i]), P.eps)));
+      if constexpr (FAST)
+        ww[i] = __fsub_rn(ww[i], __fdividef(__fmul_rn(P.lr, mm[i]), __fadd_rn(sqrt_approx(v2[i]), P.eps)));
+      else
+        ww[i] = __fsub_rn(ww[i], __fdiv_rn(__fmul_rn(P.lr, mm[i]), __fadd_rn(__fsqrt_rn(v2[i]), P.eps)));
     }
     s0v = make_float4(mm[0], mm[1], mm[2], mm[3]);
     s1v = make_float4(v2[0], v2[1], v2[2], v2[3]);
@@ -112,398 +143,516 @@ __device__ __forceinline__ void opt_step4(const UpdParams& P, float4& wv, float4
   wv = make_float4(ww[0], ww[1], ww[2], ww[3]);
 }
 
-// Apply the optimizer to up to N rows at once: all row loads (table + slots) are
-// issued before the first use, so N*(1+slots) 128-bit loads are in flight per lane.
-template <int V, int N, int OPT>
-__device__ __forceinline__ bool apply_rows(const UpdParams& P, const UpdFeat& F, unsigned mask,
-                                           const uint32_t (&key)[N], const float4 (&g)[N][V],
-                                           const int (&col)[V], const bool (&act)[V]) {
-  bool all_ok = true;
-  bool ok[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    ok[i] = (mask >> i) & 1u;
-    if (ok[i] && key[i] == 0xFFFFFFFFu) ok[i] = false;  // padding entry (sharded path)
-    if (ok[i] && (uint64_t)key[i] >= (uint64_t)F.rows) { ok[i] = false; all_ok = false; }
-  }
-  float4 w[N][V], s0[N][V], s1[N][V];
-#pragma unroll
-  for (int i = 0; i < N; ++i)
+// bag (= gradient row) of sorted entry i
+__device__ __forceinline__ int entry_bag(const UpdFeat& F, int i) {
+  const int v = F.vals[i];
+  return F.pos2bag != nullptr ? F.pos2bag[v] : v;
+}
+
+// gradient scale of the pooled lookup's backward: mean -> 1/count, sqrtn -> 1/sqrt(count)
+__device__ __forceinline__ float bag_scale(const UpdFeat& F, int bag) {
+  const int64_t c = F.offsets[bag + 1] - F.offsets[bag];
+  return (F.combiner == HB_MEAN) ? (float)c : __fsqrt_rn((float)c);
+}
+
+// ---- sink of one finished row sum -------------------------------------------------------
+// kModeApply: read-modify-write of the table row and its slots (row/slot values may
+// have been prefetched into w/s0/s1).  kModeEmit: store the sum into the owner's
+// grads_in window at the slot of unique `u` (requester side of the sharded backward).
+template <int V, int MODE>
+__device__ __forceinline__ float* emit_dst(const UpdParams& P, const UpdFeat& F, int u) {
+  int r = 0;
+  while (r + 1 < P.emit.world && F.emit_send_off[r + 1] <= u) ++r;
+  const int drow = F.emit_remote_base[r] + (u - F.emit_send_off[r]);
+  if (drow >= F.emit_cap) return nullptr;  // overflow already flagged by the exchange
+  return reinterpret_cast<float*>(P.emit.peers.p[r] + P.emit.window_off + F.emit_off) + (int64_t)drow * F.dim;
+}
+
+template <int V, int OPT, int MODE, bool FAST>
+__device__ __forceinline__ void sink_row(const UpdParams& P, const UpdFeat& F, uint32_t key, int u,
+                                         const float4 (&acc)[V], const int (&col)[V],
+                                         const bool (&act)[V], bool& oob) {
+  if constexpr (MODE == kModeApply) {
+    if ((uint64_t)key >= (uint64_t)F.rows) { oob = true; return; }
+    float4 w[V], s0[V], s1[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      w[i][v] = s0[i][v] = s1[i][v] = f4_zero();
-      if (ok[i] && act[v]) {
-        const int64_t o = (int64_t)key[i] * F.dim + col[v];
-        w[i][v] = *reinterpret_cast<const float4*>(F.table + o);
-        if constexpr (OPT != HB_OPT_SGD) s0[i][v] = *reinterpret_cast<const float4*>(F.slot0 + o);
-        if constexpr (OPT == HB_OPT_LAZY_ADAM) s1[i][v] = *reinterpret_cast<const float4*>(F.slot1 + o);
+      w[v] = s0[v] = s1[v] = f4_zero();
+      if (act[v]) {
+        const int64_t o = (int64_t)key * F.dim + col[v];
+        w[v] = *reinterpret_cast<const float4*>(F.table + o);
+        if constexpr (OPT != HB_OPT_SGD) s0[v] = *reinterpret_cast<const float4*>(F.slot0 + o);
+        if constexpr (OPT == HB_OPT_LAZY_ADAM) s1[v] = *reinterpret_cast<const float4*>(F.slot1 + o);
       }
     }
 #pragma unroll
-  for (int i = 0; i < N; ++i)
+    for (int v = 0; v < V; ++v)
+      if (act[v]) {
+        const int64_t o = (int64_t)key * F.dim + col[v];
+        opt_step4<OPT, FAST>(P, w[v], s0[v], s1[v], acc[v]);
+        *reinterpret_cast<float4*>(F.table + o) = w[v];
+        if constexpr (OPT != HB_OPT_SGD) *reinterpret_cast<float4*>(F.slot0 + o) = s0[v];
+        if constexpr (OPT == HB_OPT_LAZY_ADAM) *reinterpret_cast<float4*>(F.slot1 + o) = s1[v];
+      }
+  } else {
+    float* dst = emit_dst<V, MODE>(P, F, u);
+    if (dst == nullptr) return;
 #pragma unroll
     for (int v = 0; v < V; ++v)
-      if (ok[i] && act[v]) {
-        const int64_t o = (int64_t)key[i] * F.dim + col[v];
-        opt_step4<OPT>(P, w[i][v], s0[i][v], s1[i][v], g[i][v]);
-        *reinterpret_cast<float4*>(F.table + o) = w[i][v];
-        if constexpr (OPT != HB_OPT_SGD) *reinterpret_cast<float4*>(F.slot0 + o) = s0[i][v];
-        if constexpr (OPT == HB_OPT_LAZY_ADAM) *reinterpret_cast<float4*>(F.slot1 + o) = s1[i][v];
-      }
-  return all_ok;
-}
-
-template <int V, int OPT>
-__device__ __forceinline__ bool apply_row(const UpdParams& P, const UpdFeat& F, uint32_t key,
-                                          const float4 (&acc)[V], const int (&col)[V],
-                                          const bool (&act)[V]) {
-  const uint32_t k1[1] = {key};
-  float4 g1[1][V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) g1[0][v] = acc[v];
-  return apply_rows<V, 1, OPT>(P, F, 1u, k1, g1, col, act);
-}
-
-// A warp owns 32 consecutive sorted entries (lane e holds key/bag of entry e: one
-// coalesced load each); the run structure of the warp tile is a pair of ballot
-// masks.  Each of the 32/G groups walks its G consecutive entries in sub-batches
-// of SB: the gradient rows AND the table/slot rows of the runs ending in the
-// sub-batch are loaded together (one memory round trip), summed in position
-// order, and applied.  smem per CTA: groups * (2*V*G float4 partials + 2 keys + flag).
-template <int V, int OPT>
-__global__ void __launch_bounds__(kUpdThreads, (V == 1 ? 3 : 1))
-sparse_update_kernel(const __grid_constant__ UpdParams P) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  wait_spec(P.wait, P.status);
-  const int fi = find_upd_feat(P, blockIdx.x);
-  const UpdFeat& F = P.f[fi];
-  const int st = blockIdx.x - F.cta_begin;
-  const int log2g = F.log2g;
-  const int G = 1 << log2g;
-  const int groups = kUpdThreads >> log2g;
-  const int g = threadIdx.x >> log2g;
-  const int l = threadIdx.x & (G - 1);
-  const int dim = F.dim;
-  int n = F.n;
-  if (F.n_dev != nullptr) { const int d = *F.n_dev; n = d < 0 ? 0 : (d < n ? d : n); }
-  // smem carve-up
-  float4* s_part = reinterpret_cast<float4*>(s_raw);                  // [groups][2][V][G]
-  uint32_t* s_key = reinterpret_cast<uint32_t*>(s_part + (size_t)groups * 2 * V * G);  // [groups][2]
-  int32_t* s_flag = reinterpret_cast<int32_t*>(s_key + groups * 2);   // [groups]
-
-  int col[V];
-  bool act[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    col[v] = ((v << log2g) + l) * 4;
-    act[v] = col[v] < dim;
+      if (act[v]) *reinterpret_cast<float4*>(dst + col[v]) = acc[v];
   }
+}
+
+// ---- dense work map ---------------------------------------------------------------------
+// Work units per feature are data dependent (unique counts, device-side lengths):
+// every CTA scans them into shared memory once and walks the dense unit list, so
+// no CTA is ever launched for (or iterates over) work that does not exist.
+__device__ __forceinline__ int seg_scan(int nsegs, int my_units, int* s_begin /*[kMaxSegs + 1]*/) {
+  if ((int)threadIdx.x < nsegs) s_begin[threadIdx.x] = my_units;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int carry = 0;
+    for (int b = 0; b < nsegs; b += 32) {
+      const int i = b + (int)threadIdx.x;
+      const int v = i < nsegs ? s_begin[i] : 0;
+      int incl = v;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, off);
+        if ((int)threadIdx.x >= off) incl += y;
+      }
+      if (i < nsegs) s_begin[i] = carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (threadIdx.x == 0) s_begin[nsegs] = carry;
+  }
+  __syncthreads();
+  return s_begin[nsegs];
+}
+
+__device__ __forceinline__ int seg_find(const int* s_begin, int nsegs, int unit) {
+  int lo = 0, hi = nsegs - 1;
+  while (lo < hi) {  // last seg with begin <= unit (empty segs are skipped)
+    const int mid = (lo + hi + 1) >> 1;
+    if (s_begin[mid] <= unit) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// ---- 3. runs ----------------------------------------------------------------------------
+constexpr int kRunItems = 8;
+constexpr int kRunTile = kUpdThreads * kRunItems;  // 2048
+
+struct RunFeat {
+  const uint32_t* keys;   // sorted
+  const int32_t* vals;
+  uint32_t* ukey;
+  int32_t* ustart;
+  int32_t* counts;        // [0] = U, [1] = valid entries
+  int32_t* inv;           // may be nullptr
+  int32_t* owner_start1;  // may be nullptr
+  const int32_t* n_dev;
+  int32_t n;
+  int32_t lbits;
+};
+
+struct RunParams {
+  RunFeat f[kMaxUpdFeats];
+  uint32_t* status;   // [sum of static tiles + nfeats], zeroed
+  uint32_t* ticket;   // zeroed
+  int32_t* d_status;
+  int32_t nfeats;
+};
+
+__device__ __forceinline__ int run_len(const RunFeat& F) {
+  if (F.n_dev == nullptr) return F.n;
+  const int d = *F.n_dev;
+  return d < 0 ? 0 : (d < F.n ? d : F.n);
+}
+
+__global__ void __launch_bounds__(kUpdThreads) runs_kernel(const __grid_constant__ RunParams P) {
+  __shared__ int s_begin[kMaxUpdFeats + 1];
+  __shared__ int32_t s_scan[kBucketWarps];
+  __shared__ int s_tile;
+  const int tid = threadIdx.x;
+  int units = 0;
+  if (tid < P.nfeats) {
+    const int n = run_len(P.f[tid]);
+    units = (n + kRunTile - 1) / kRunTile;
+    if (units < 1) units = 1;  // an empty feature still publishes U = 0
+  }
+  const int total = seg_scan(P.nfeats, units, s_begin);
   bool oob = false;
-  int flag = 0;
-
-  // ---- warp tile: 32 entries, lane e <-> entry e -------------------------------
-  const unsigned lane = lane_id();
-  const int warp = threadIdx.x >> 5;
-  const int64_t w0 = ((int64_t)st * (kUpdThreads / 32) + warp) * 32;  // first entry of the warp
-  const int wcnt = (int)max((int64_t)0, min((int64_t)32, (int64_t)n - w0));
-  uint32_t my_key = 0xFFFFFFFFu;
-  int32_t my_bag = 0;
-  if ((int)lane < wcnt) { my_key = F.keys[w0 + lane]; my_bag = F.bags[w0 + lane]; }
-  // neighbours of the warp tile
-  uint32_t edge_key = 0;
-  bool edge_has = false;
-  if (lane == 0 && wcnt > 0 && w0 > 0) { edge_key = F.keys[w0 - 1]; edge_has = true; }
-  if (lane == 31 && wcnt == 32 && w0 + 32 < n) { edge_key = F.keys[w0 + 32]; edge_has = true; }
-  float my_scale = 1.0f;
-  const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
-  if (scaled && (int)lane < wcnt) {
-    const int64_t c = F.offsets[my_bag + 1] - F.offsets[my_bag];
-    my_scale = (F.combiner == HB_MEAN) ? (float)c : __fsqrt_rn((float)c);
-  }
-  // same_prev bit e: entry e has the same key as entry e-1 (globally)
-  const uint32_t up_key = __shfl_up_sync(0xffffffffu, my_key, 1);
-  bool sp = false;
-  if ((int)lane < wcnt) sp = (lane == 0) ? (edge_has && edge_key == my_key) : (up_key == my_key);
-  const unsigned same_prev = __ballot_sync(0xffffffffu, sp);
-  // does the run of the warp's last entry continue in the next warp tile?
-  const unsigned cont_next = __ballot_sync(0xffffffffu, lane == 31 && edge_has && edge_key == my_key);
-  const bool warp_open_right = cont_next != 0;
-
-  // ---- group tile: C = G consecutive entries of the warp tile --------------------
-  constexpr int SB = (V == 1) ? 4 : (V == 2 ? 2 : 1);
-  const int gw = (lane >> log2g);     // group index inside the warp
-  const int c0 = gw * G;              // first warp-entry of my group
-  const int cnt = max(0, min(G, wcnt - c0));
-  float4* my_part = s_part + (size_t)g * 2 * V * G;
-  if (wcnt > 0) {  // warp-uniform: every lane takes part in the shuffles below
-    const bool first_open_left = (same_prev >> c0) & 1u;
-    bool seen_tail = false;
-    float4 carry[V];
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_tile = (int)atomicAdd(P.ticket, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= total) break;
+    const int fi = seg_find(s_begin, P.nfeats, tile);
+    const RunFeat& F = P.f[fi];
+    const int t = tile - s_begin[fi];
+    const int n = run_len(F);
+    const int i0 = t * kRunTile + tid * kRunItems;
+    // k[0] = key of the entry before mine, k[1..8] mine, k[9] the one after
+    uint32_t k[kRunItems + 2];
 #pragma unroll
-    for (int v = 0; v < V; ++v) carry[v] = f4_zero();
-    // trip count G/SB is the same for every group of the warp (groups with fewer
-    // valid entries run predicated-off iterations)
-#pragma unroll 1
-    for (int j0 = 0; j0 < G; j0 += SB) {
-      uint32_t k[SB];
-      bool valid[SB], head[SB], is_apply[SB];
-      int part_slot[SB];  // -1 none, 0 first-open partial, 1 last-open partial
-      int part_flag[SB];
-      unsigned apply_mask = 0;
-      float4 gv[SB][V];
-      float sc[SB];
+    for (int j = 0; j < kRunItems + 2; ++j) {
+      const int i = i0 - 1 + j;
+      k[j] = (i >= 0 && i < n) ? F.keys[i] : 0xFFFFFFFFu;
+    }
+    bool head[kRunItems];
+    int cnt = 0;
 #pragma unroll
-      for (int i = 0; i < SB; ++i) {
-        const int e = c0 + j0 + i;                 // entry index inside the warp tile
-        valid[i] = (j0 + i) < cnt;
-        const int src = valid[i] ? e : c0;
-        k[i] = __shfl_sync(0xffffffffu, my_key, src);
-        const int32_t bag = __shfl_sync(0xffffffffu, my_bag, src);
-        sc[i] = __shfl_sync(0xffffffffu, my_scale, src);
-        head[i] = !((same_prev >> src) & 1u);
-        is_apply[i] = false;
-        part_slot[i] = -1;
-        part_flag[i] = 0;
-        if (valid[i]) {
-          const bool last = (j0 + i == cnt - 1);
-          // tail: the next entry (inside the warp tile, or beyond it) starts a new run
-          bool next_same;
-          if (e + 1 < wcnt) next_same = (same_prev >> (e + 1)) & 1u;
-          else next_same = warp_open_right;        // e is the warp tile's last entry
-          const bool tail = !next_same || last;
-          if (tail) {
-            const bool ol = first_open_left && !seen_tail;
-            const bool orr = last && next_same;
-            if (!ol && !orr) { is_apply[i] = true; apply_mask |= 1u << i; }
-            else if (ol) { part_slot[i] = 0; part_flag[i] = kFirstOpen | (orr ? kBoth : 0); }
-            else { part_slot[i] = 1; part_flag[i] = kLastOpen; }
-            seen_tail = true;
-          }
+    for (int j = 0; j < kRunItems; ++j) {
+      const int i = i0 + j;
+      const bool valid = i < n && k[j + 1] < 0xFFFFFFFEu;
+      if (i < n && k[j + 1] == 0xFFFFFFFEu) oob = true;
+      head[j] = valid && (i == 0 || k[j + 1] != k[j]);
+      cnt += head[j] ? 1 : 0;
+    }
+    int32_t tile_total;
+    const int32_t excl = block_excl_scan(cnt, s_scan, &tile_total);
+    if (tid == 0)
+      *reinterpret_cast<volatile uint32_t*>(&P.status[tile]) = (uint32_t)tile_total | kReady;
+    // uniques in the preceding tiles of this feature
+    int32_t pre = 0;
+    for (int tp = tid; tp < t; tp += kUpdThreads) {
+      const uint32_t* w = P.status + s_begin[fi] + tp;
+      uint32_t v = ld_volatile_u32(w);
+      while (!(v & kReady)) v = ld_volatile_u32(w);
+      pre += (int32_t)(v & ~kReady);
+    }
+    int32_t pre_total;
+    block_excl_scan(pre, s_scan, &pre_total);
+    int u = pre_total + excl;  // index the next head of this thread gets
 #pragma unroll
-          for (int v = 0; v < V; ++v) {
-            gv[i][v] = f4_zero();
-            if (act[v])
-              gv[i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
-                  F.grad + (int64_t)bag * F.grad_stride + col[v]));
-          }
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; ++v) gv[i][v] = f4_zero();
+    for (int j = 0; j < kRunItems; ++j) {
+      const int i = i0 + j;
+      if (i >= n) break;
+      const bool valid = k[j + 1] < 0xFFFFFFFEu;
+      if (head[j]) {
+        F.ukey[u] = k[j + 1];
+        F.ustart[u] = i;
+        if (F.owner_start1 != nullptr) {
+          const uint32_t own = k[j + 1] >> F.lbits;
+          if (i == 0 || (k[j] >> F.lbits) != own) F.owner_start1[own] = u + 1;
         }
+        ++u;
       }
-      // table / slot rows of the runs that end (closed) in this sub-batch: issued
-      // right behind the gradient loads, consumed after the sums
-      bool ok[SB];
-      float4 w[SB][V], s0[SB][V], s1[SB][V];
+      if (F.inv != nullptr) F.inv[F.vals[i]] = valid ? u - 1 : -1;
+      if (valid && (i + 1 >= n || k[j + 2] >= 0xFFFFFFFEu)) {  // last valid entry of the feature
+        F.ustart[u] = i + 1;
+        F.counts[0] = u;
+        F.counts[1] = i + 1;
+      }
+    }
+    if (t == 0 && tid == 0 && (n == 0 || k[1] >= 0xFFFFFFFEu)) {  // no valid entry at all
+      F.ustart[0] = 0;
+      F.counts[0] = 0;
+      F.counts[1] = 0;
+    }
+  }
+  if (oob) raise_status(P.d_status, HB_STATUS_ID_OUT_OF_RANGE);
+}
+
+// ---- 4. short runs ----------------------------------------------------------------------
+__device__ __forceinline__ void queue_long(const UpdParams& P, int fi, int u, int len) {
+  const int np = (len + kPiece - 1) / kPiece;
+  const int base = atomicAdd(&P.long_count[0], np);
+  const int pb = np > 1 ? atomicAdd(&P.long_count[1], np) : -1;
+  if (base + np > P.item_cap || (np > 1 && pb + np > P.part_cap)) {  // cannot happen by the layout bounds
+    raise_status(P.status, HB_STATUS_WINDOW_OVERFLOW);
+    return;
+  }
+  for (int j = 0; j < np; ++j) P.items[base + j] = LongItem{fi, u, j, pb};
+}
+
+template <int V, int OPT, int MODE, bool FAST>
+__global__ void __launch_bounds__(kUpdThreads, (V == 1 ? 3 : (V == 2 ? 2 : 1)))
+update_short_kernel(const __grid_constant__ UpdParams P) {
+  __shared__ int s_begin[kMaxUpdFeats + 1];
+  wait_spec(P.wait, P.status);
+  const int tid = threadIdx.x;
+  int units = 0;
+  if (tid < P.nfeats) {
+    const int uc = (kUpdThreads >> P.f[tid].log2g) * kNU;
+    units = (P.f[tid].counts[0] + uc - 1) / uc;
+    if (units > P.f[tid].max_chunks) units = P.f[tid].max_chunks;
+  }
+  const int total = seg_scan(P.nfeats, units, s_begin);
+  bool oob = false;
+  for (int chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+    const int fi = seg_find(s_begin, P.nfeats, chunk);
+    const UpdFeat& F = P.f[fi];
+    const int log2g = F.log2g;
+    const int groups = kUpdThreads >> log2g;
+    const int g = tid >> log2g;
+    const int l = tid & ((1 << log2g) - 1);
+    const int dim = F.dim;
+    const int U = F.counts[0];
+    const int u0 = (chunk - s_begin[fi]) * groups * kNU;
+    const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
+    int col[V];
+    bool act[V];
 #pragma unroll
-      for (int i = 0; i < SB; ++i) {
-        ok[i] = is_apply[i];
-        if (ok[i] && k[i] == 0xFFFFFFFFu) ok[i] = false;                      // padding entry
-        if (ok[i] && (uint64_t)k[i] >= (uint64_t)F.rows) { ok[i] = false; oob = true; }
+    for (int v = 0; v < V; ++v) {
+      col[v] = ((v << log2g) + l) * 4;
+      act[v] = col[v] < dim;
+    }
+    // run bounds and keys of my kNU unique rows (consecutive groups <-> consecutive uniques)
+    int us[kNU], s[kNU], len[kNU];
+    uint32_t key[kNU];
+    bool ok[kNU];
+#pragma unroll
+    for (int q = 0; q < kNU; ++q) {
+      us[q] = u0 + q * groups + g;
+      ok[q] = us[q] < U;
+      const int uu = ok[q] ? us[q] : 0;
+      s[q] = F.ustart[uu];
+      len[q] = F.ustart[uu + 1] - s[q];
+      key[q] = F.ukey[uu];
+    }
+#pragma unroll
+    for (int q = 0; q < kNU; ++q) {
+      if (!ok[q]) len[q] = 0;
+      if (ok[q] && len[q] > kShortMax) {  // hot row: the long kernel sums it with whole warps
+        if (l == 0) queue_long(P, fi, us[q], len[q]);
+        ok[q] = false;
+        len[q] = 0;
+      }
+      if (MODE == kModeApply && ok[q] && (uint64_t)key[q] >= (uint64_t)F.rows) {
+        oob = true;
+        ok[q] = false;
+        len[q] = 0;
+      }
+    }
+    // table / slot rows: their addresses only need the key, so they travel together
+    // with the bag indices; the gradient rows follow one round trip later
+    float4 w[kNU][V], s0[kNU][V], s1[kNU][V];
+    if constexpr (MODE == kModeApply) {
+#pragma unroll
+      for (int q = 0; q < kNU; ++q)
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          w[i][v] = s0[i][v] = s1[i][v] = f4_zero();
-          if (ok[i] && act[v]) {
-            const int64_t o = (int64_t)k[i] * dim + col[v];
-            w[i][v] = *reinterpret_cast<const float4*>(F.table + o);
-            if constexpr (OPT != HB_OPT_SGD) s0[i][v] = *reinterpret_cast<const float4*>(F.slot0 + o);
-            if constexpr (OPT == HB_OPT_LAZY_ADAM) s1[i][v] = *reinterpret_cast<const float4*>(F.slot1 + o);
+          w[q][v] = s0[q][v] = s1[q][v] = f4_zero();
+          if (ok[q] && act[v]) {
+            const int64_t o = (int64_t)key[q] * dim + col[v];
+            w[q][v] = *reinterpret_cast<const float4*>(F.table + o);
+            if constexpr (OPT != HB_OPT_SGD) s0[q][v] = *reinterpret_cast<const float4*>(F.slot0 + o);
+            if constexpr (OPT == HB_OPT_LAZY_ADAM) s1[q][v] = *reinterpret_cast<const float4*>(F.slot1 + o);
           }
         }
+    }
+    // first two entries of every run, all in flight together (most runs end here)
+    int bag[kNU][2];
+#pragma unroll
+    for (int q = 0; q < kNU; ++q)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) bag[q][i] = (i < len[q]) ? entry_bag(F, s[q] + i) : -1;
+    float4 gv[kNU][2][V];
+    float sc[kNU][2];
+#pragma unroll
+    for (int q = 0; q < kNU; ++q)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        sc[q][i] = 1.0f;
+        if (scaled && bag[q][i] >= 0) sc[q][i] = bag_scale(F, bag[q][i]);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          gv[q][i][v] = f4_zero();
+          if (bag[q][i] >= 0 && act[v])
+            gv[q][i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
+                F.grad + (int64_t)bag[q][i] * F.grad_stride + col[v]));
+        }
       }
-      if (scaled) {
+    float4 acc[kNU][V];
 #pragma unroll
-        for (int i = 0; i < SB; ++i)
+    for (int q = 0; q < kNU; ++q) {
 #pragma unroll
-          for (int v = 0; v < V; ++v)
-            gv[i][v] = make_float4(__fdiv_rn(gv[i][v].x, sc[i]), __fdiv_rn(gv[i][v].y, sc[i]),
-                                   __fdiv_rn(gv[i][v].z, sc[i]), __fdiv_rn(gv[i][v].w, sc[i]));
+      for (int v = 0; v < V; ++v) {
+        // the first term is taken as is (0 + g would turn -0 into +0), later terms are
+        // added in position order
+        acc[q][v] = scaled ? f4_div_rn(gv[q][0][v], sc[q][0]) : gv[q][0][v];
+        if (len[q] > 1)
+          acc[q][v] = f4_add_rn(acc[q][v], scaled ? f4_div_rn(gv[q][1][v], sc[q][1]) : gv[q][1][v]);
       }
-      // segmented inclusive sums, in position order
+      // entries 2 .. len-1 (rare), four at a time
+      for (int j0 = 2; j0 < len[q]; j0 += 4) {
+        int b4[4];
 #pragma unroll
-      for (int i = 0; i < SB; ++i) {
-        if (valid[i]) {
-          const bool cont = (j0 + i == 0) ? false : !head[i];  // continues a run of THIS group tile
-          if (cont) {
+        for (int i = 0; i < 4; ++i) b4[i] = (j0 + i < len[q]) ? entry_bag(F, s[q] + j0 + i) : -1;
+        float4 x[4][V];
+        float c4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          c4[i] = 1.0f;
+          if (scaled && b4[i] >= 0) c4[i] = bag_scale(F, b4[i]);
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            x[i][v] = f4_zero();
+            if (b4[i] >= 0 && act[v])
+              x[i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
+                  F.grad + (int64_t)b4[i] * F.grad_stride + col[v]));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (b4[i] >= 0)
 #pragma unroll
             for (int v = 0; v < V; ++v)
-              gv[i][v] = f4_add_rn(i == 0 ? carry[v] : gv[i > 0 ? i - 1 : 0][v], gv[i][v]);
-          }
-        }
-      }
-      // run ends: apply or park the partial sum
-#pragma unroll
-      for (int i = 0; i < SB; ++i) {
-        if (ok[i]) {
-#pragma unroll
-          for (int v = 0; v < V; ++v)
-            if (act[v]) {
-              const int64_t o = (int64_t)k[i] * dim + col[v];
-              opt_step4<OPT>(P, w[i][v], s0[i][v], s1[i][v], gv[i][v]);
-              *reinterpret_cast<float4*>(F.table + o) = w[i][v];
-              if constexpr (OPT != HB_OPT_SGD) *reinterpret_cast<float4*>(F.slot0 + o) = s0[i][v];
-              if constexpr (OPT == HB_OPT_LAZY_ADAM) *reinterpret_cast<float4*>(F.slot1 + o) = s1[i][v];
-            }
-        } else if (part_slot[i] >= 0) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) my_part[(part_slot[i] * V + v) * G + l] = gv[i][v];
-          if (l == 0) s_key[g * 2 + part_slot[i]] = k[i];
-          flag |= part_flag[i];
-        }
-      }
-#pragma unroll
-      for (int v = 0; v < V; ++v) carry[v] = gv[SB - 1][v];
-    }
-  }
-  __shared__ int s_stflag;
-  if (threadIdx.x == 0) s_stflag = 0;
-  if (l == 0) s_flag[g] = flag;
-  __syncthreads();
-
-  // ---- combine runs crossing tile borders inside the super-tile -------------
-  float* gpart = F.st_part + (size_t)st * 2 * dim;
-  int st_flag = 0;
-  if (g == 0 && (flag & kFirstOpen)) {
-    // chain entering from the previous super-tile
-    float4 acc[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = s_part[(size_t)(0 * 2 + 0) * V * G + v * G + l];
-    int t = 0;
-    bool both = true;
-    while (true) {
-      if (!(s_flag[t] & kBoth)) { both = false; break; }
-      ++t;
-      if (t == groups || !(s_flag[t] & kFirstOpen)) break;  // leaves the super-tile
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-        acc[v] = f4_add_rn(acc[v], s_part[(size_t)(t * 2 + 0) * V * G + v * G + l]);
-    }
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-      if (act[v]) *reinterpret_cast<float4*>(gpart + 0 * dim + col[v]) = acc[v];
-    if (l == 0) F.st_key[(size_t)st * 2 + 0] = s_key[0];
-    st_flag |= kFirstOpen | (both ? kBoth : 0);
-  }
-  if (flag & kLastOpen) {
-    // chain starting in my tile
-    float4 acc[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = s_part[(size_t)(g * 2 + 1) * V * G + v * G + l];
-    const uint32_t key = s_key[g * 2 + 1];
-    int t = g + 1;
-    bool closed = false;
-    while (t < groups) {
-      if (!(s_flag[t] & kFirstOpen)) break;  // (empty tail tile) -- cannot happen when open
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-        acc[v] = f4_add_rn(acc[v], s_part[(size_t)(t * 2 + 0) * V * G + v * G + l]);
-      if (!(s_flag[t] & kBoth)) { closed = true; break; }
-      ++t;
-    }
-    if (closed) {
-      if (!apply_row<V, OPT>(P, F, key, acc, col, act)) oob = true;
-    } else {
-      // still open at the end of the super-tile
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (act[v]) *reinterpret_cast<float4*>(gpart + 1 * dim + col[v]) = acc[v];
-      if (l == 0) {
-        F.st_key[(size_t)st * 2 + 1] = key;
-        atomicOr(&s_stflag, kLastOpen);
+              acc[q][v] = f4_add_rn(acc[q][v], scaled ? f4_div_rn(x[i][v], c4[i]) : x[i][v]);
       }
     }
-  }
-  if (g == 0 && l == 0 && st_flag) atomicOr(&s_stflag, st_flag);
-  if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
-  __syncthreads();
-  if (threadIdx.x == 0) F.st_flag[st] = s_stflag;
-}
-
-// Finish rows that span super-tiles (hot keys): one WARP per super-tile that
-// starts a chain.  Per round the warp reads the flags of the next 32 super-tiles
-// with one coalesced load and finds the chain end with a ballot; its 32/G groups
-// then sum the partial rows t+gi, t+gi+ng, ... (independent loads), and the group
-// sums are combined in a fixed order with shuffles.  Order of addition is a fixed
-// function of the chain length => deterministic.
-template <int V, int OPT>
-__global__ void __launch_bounds__(kUpdThreads)
-sparse_update_fixup_kernel(const __grid_constant__ UpdParams P) {
-  const int fi = find_upd_feat(P, blockIdx.x);
-  const UpdFeat& F = P.f[fi];
-  const int log2g = F.log2g;
-  const int G = 1 << log2g;
-  const int ng = 32 >> log2g;            // groups per warp
-  const unsigned lane = lane_id();
-  const int gi = lane >> log2g;          // my group inside the warp
-  const int l = lane & (G - 1);
-  const int dim = F.dim;
-  const int st = (blockIdx.x - F.cta_begin) * (kUpdThreads / 32) + (threadIdx.x >> 5);
-  if (st >= F.nst) return;               // warp-uniform
-  if (!(F.st_flag[st] & kLastOpen)) return;
-  int col[V];
-  bool act[V];
+    // sink
 #pragma unroll
-  for (int v = 0; v < V; ++v) {
-    col[v] = ((v << log2g) + l) * 4;
-    act[v] = col[v] < dim;
-  }
-  // group 0 starts from the chain head's partial, the others from zero
-  float4 acc[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v)
-    acc[v] = (gi == 0 && act[v])
-                 ? *reinterpret_cast<const float4*>(F.st_part + ((size_t)st * 2 + 1) * dim + col[v])
-                 : f4_zero();
-  const uint32_t key = F.st_key[(size_t)st * 2 + 1];
-  int t = st + 1;
-  bool done = false;
-  while (!done && t < F.nst) {
-    // flags of super-tiles t .. t+31
-    const int fl = (t + (int)lane < F.nst) ? F.st_flag[t + lane] : 0;
-    const unsigned is_first = __ballot_sync(0xffffffffu, (fl & kFirstOpen) != 0);
-    const unsigned is_both = __ballot_sync(0xffffffffu, (fl & kBoth) != 0);
-    // chain covers tiles while FirstOpen; it ends after the first one without Both
-    const unsigned stop_a = ~is_first;            // tile does not continue the chain at all
-    const unsigned stop_b = is_first & ~is_both;  // last tile of the chain (included)
-    int m;                                        // number of tiles of this round to add
-    const int pa = stop_a ? __ffs(stop_a) - 1 : 32;
-    const int pb = stop_b ? __ffs(stop_b) - 1 : 32;
-    if (pb < pa) { m = pb + 1; done = true; }
-    else { m = pa; if (pa < 32) done = true; }
-    // my group adds tiles t+gi, t+gi+ng, ... (< t+m), 8 loads in flight
-    for (int u0 = gi; u0 < m; u0 += ng * 8) {
-      float4 x[8][V];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int u = u0 + j * ng;
+    for (int q = 0; q < kNU; ++q) {
+      if (!ok[q]) continue;
+      if constexpr (MODE == kModeApply) {
 #pragma unroll
         for (int v = 0; v < V; ++v)
-          x[j][v] = (u < m && act[v])
-                        ? *reinterpret_cast<const float4*>(F.st_part + ((size_t)(t + u) * 2 + 0) * dim + col[v])
-                        : f4_zero();
+          if (act[v]) {
+            const int64_t o = (int64_t)key[q] * dim + col[v];
+            opt_step4<OPT, FAST>(P, w[q][v], s0[q][v], s1[q][v], acc[q][v]);
+            *reinterpret_cast<float4*>(F.table + o) = w[q][v];
+            if constexpr (OPT != HB_OPT_SGD) *reinterpret_cast<float4*>(F.slot0 + o) = s0[q][v];
+            if constexpr (OPT == HB_OPT_LAZY_ADAM) *reinterpret_cast<float4*>(F.slot1 + o) = s1[q][v];
+          }
+      } else {
+        sink_row<V, OPT, MODE, FAST>(P, F, key[q], us[q], acc[q], col, act, oob);
+      }
+    }
+  }
+  if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
+}
+
+// ---- 5. long runs -----------------------------------------------------------------------
+template <int V, int OPT, int MODE, bool FAST>
+__global__ void __launch_bounds__(kUpdThreads, (V == 1 ? 2 : 1))
+update_long_kernel(const __grid_constant__ UpdParams P) {
+  constexpr int kBatch = (V == 1) ? 8 : (V == 2 ? 4 : 2);  // gradient rows in flight per group
+  const unsigned lane = lane_id();
+  const int warps_per_cta = kUpdThreads / 32;
+  int total = P.long_count[0];
+  if (total > P.item_cap) total = P.item_cap;
+  bool oob = false;
+  for (int it = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); it < total;
+       it += gridDim.x * warps_per_cta) {
+    const LongItem item = P.items[it];
+    const UpdFeat& F = P.f[item.feat];
+    const int log2g = F.log2g;
+    const int G = 1 << log2g;
+    const int ng = 32 >> log2g;        // groups per warp
+    const int gi = lane >> log2g;
+    const int l = lane & (G - 1);
+    const int dim = F.dim;
+    const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
+    int col[V];
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      col[v] = ((v << log2g) + l) * 4;
+      act[v] = col[v] < dim;
+    }
+    const int rs = F.ustart[item.u];
+    const int re = F.ustart[item.u + 1];
+    const int np = (re - rs + kPiece - 1) / kPiece;
+    const int s = rs + item.piece * kPiece;
+    const int m = min(kPiece, re - s);
+    const uint32_t key = F.ukey[item.u];
+    // group gi sums entries gi, gi + ng, gi + 2 ng, ... of the piece, in that order
+    float4 acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = f4_zero();
+    bool first = true;
+    for (int j0 = 0; j0 < m; j0 += ng * kBatch) {  // warp-uniform trip count
+      int bag[kBatch];
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        const int j = j0 + i * ng + gi;
+        bag[i] = j < m ? entry_bag(F, s + j) : -1;
+      }
+      float4 x[kBatch][V];
+      float c[kBatch];
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        c[i] = 1.0f;
+        if (scaled && bag[i] >= 0) c[i] = bag_scale(F, bag[i]);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          x[i][v] = f4_zero();
+          if (bag[i] >= 0 && act[v])
+            x[i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
+                F.grad + (int64_t)bag[i] * F.grad_stride + col[v]));
+        }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (u0 + j * ng < m)
+      for (int i = 0; i < kBatch; ++i)
+        if (bag[i] >= 0) {
 #pragma unroll
-          for (int v = 0; v < V; ++v) acc[v] = f4_add_rn(acc[v], x[j][v]);
+          for (int v = 0; v < V; ++v) {
+            const float4 t = scaled ? f4_div_rn(x[i][v], c[i]) : x[i][v];
+            acc[v] = first ? t : f4_add_rn(acc[v], t);
+          }
+          first = false;
+        }
     }
-    t += 32;
-  }
-  // combine the group sums in a fixed order: lanes of group gi add group gi+off
+    // group sums -> piece sum, fixed order: g0 += g(ng/2) ... (groups beyond the
+    // piece hold zeros; m >= ng is not required)
 #pragma unroll
-  for (int v = 0; v < V; ++v) {
-    for (int off = ng >> 1; off >= 1; off >>= 1) {
-      float4 y;
-      y.x = __shfl_down_sync(0xffffffffu, acc[v].x, off << log2g);
-      y.y = __shfl_down_sync(0xffffffffu, acc[v].y, off << log2g);
-      y.z = __shfl_down_sync(0xffffffffu, acc[v].z, off << log2g);
-      y.w = __shfl_down_sync(0xffffffffu, acc[v].w, off << log2g);
-      if (gi < off) acc[v] = f4_add_rn(acc[v], y);
+    for (int v = 0; v < V; ++v)
+      for (int off = ng >> 1; off >= 1; off >>= 1) {
+        float4 y;
+        y.x = __shfl_down_sync(0xffffffffu, acc[v].x, off << log2g);
+        y.y = __shfl_down_sync(0xffffffffu, acc[v].y, off << log2g);
+        y.z = __shfl_down_sync(0xffffffffu, acc[v].z, off << log2g);
+        y.w = __shfl_down_sync(0xffffffffu, acc[v].w, off << log2g);
+        if (gi < off) acc[v] = f4_add_rn(acc[v], y);
+      }
+    if (np == 1) {
+      if (gi == 0) sink_row<V, OPT, MODE, FAST>(P, F, key, item.u, acc, col, act, oob);
+      continue;
+    }
+    // multi-piece run: park the piece sum; the warp arriving last adds all pieces in
+    // piece order (which warp that is does not change the order of the additions)
+    float* prow = P.part + (size_t)(item.pbase + item.piece) * P.part_stride;
+    if (gi == 0) {
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (act[v]) *reinterpret_cast<float4*>(prow + col[v]) = acc[v];
+    }
+    __threadfence();
+    __syncwarp();
+    int old = 0;
+    if (lane == 0) old = atomicAdd(&P.tickets[item.pbase], 1);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old != np - 1) continue;  // warp-uniform
+    __threadfence();
+    if (gi == 0) {
+      const float* p0 = P.part + (size_t)item.pbase * P.part_stride;
+      float4 tot[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        tot[v] = act[v] ? ld_cg_f4(reinterpret_cast<const float4*>(p0 + col[v])) : f4_zero();
+      for (int j0 = 1; j0 < np; j0 += kBatch) {
+        float4 x[kBatch][V];
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i)
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            x[i][v] = (j0 + i < np && act[v])
+                          ? ld_cg_f4(reinterpret_cast<const float4*>(p0 + (size_t)(j0 + i) * P.part_stride + col[v]))
+                          : f4_zero();
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i)
+          if (j0 + i < np)
+#pragma unroll
+            for (int v = 0; v < V; ++v) tot[v] = f4_add_rn(tot[v], x[i][v]);
+      }
+      sink_row<V, OPT, MODE, FAST>(P, F, key, item.u, tot, col, act, oob);
     }
   }
-  if (gi == 0)
-    if (!apply_row<V, OPT>(P, F, key, acc, col, act)) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
+  if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
 }
 
 // bag index of every id position, for CSR features (thread per bag).
@@ -552,11 +701,10 @@ static void upd_shape(int dim, int* log2g, int* v) {
 constexpr int kRadixBits = 9;
 constexpr int kRadixBins = 1 << kRadixBits;
 
-
-// per-feature workspace layout
+// per-feature workspace layout (a function of nnz, dim and offsets != NULL only)
 struct UpdLayout {
-  size_t keysA, keysB, valsA, valsB, bagmap, st_part, st_key, st_flag, end;
-  int passes, log2g, V, C, nst;
+  size_t keysA, keysB, valsA, valsB, bagmap, ukey, ustart, counts, end;
+  int log2g, V;
 };
 
 static UpdLayout upd_layout(const hbUpdateFeature& f, size_t base) {
@@ -567,121 +715,223 @@ static UpdLayout upd_layout(const hbUpdateFeature& f, size_t base) {
   L.keysA = take(4 * n); L.keysB = take(4 * n);
   L.valsA = take(4 * n); L.valsB = take(4 * n);
   L.bagmap = take(f.offsets ? 4 * n : 0);
+  L.ukey = take(4 * n);
+  L.ustart = take(4 * (n + 1));
+  L.counts = take(64);
   upd_shape(f.dim, &L.log2g, &L.V);
-  L.C = 1 << L.log2g;  // entries per group: a warp owns 32 entries, a CTA 256
-  const int64_t per_st = kUpdThreads;
-  L.nst = (int)((f.nnz + per_st - 1) / per_st);
-  L.st_part = take((size_t)L.nst * 2 * f.dim * 4);
-  L.st_key = take((size_t)L.nst * 2 * 4);
-  L.st_flag = take((size_t)L.nst * 4);
-  const int64_t local_rows = f.rows;
-  const int bits = local_rows > 1 ? ilog2c(local_rows) : 1;
-  L.passes = (bits + kRadixBits - 1) / kRadixBits;
-  if (L.passes < 1) L.passes = 1;
   L.end = o;
   return L;
 }
 
-template <int V, int OPT>
-static int launch_update_opt(const UpdParams& P, const UpdParams& X, cudaStream_t stream) {
-  // smem: groups*(2*V*G*16 + 12) with groups*G == 256
-  const size_t smem = (size_t)2 * V * kUpdThreads * 16 + (size_t)kUpdThreads * 12;
-  if (smem > 48 * 1024)
-    HB_CUDA_OK(cudaFuncSetAttribute(sparse_update_kernel<V, OPT>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (P.total_ctas > 0) {
+// chunk-shared scratch behind the per-feature regions
+struct SharedLayout {
+  size_t zero_sort, zero_sort_bytes;    // bucket scratch + run status/ticket: zeroed per sort
+  size_t bucket, run_status, run_ticket;
+  size_t zero_apply, zero_apply_bytes;  // long-run counters + tickets: zeroed per apply
+  size_t long_count, tickets;
+  size_t items, part;
+  size_t end;
+  int item_cap, part_cap, part_stride;
+};
+
+static SharedLayout shared_layout(size_t base, int nc, size_t total_tiles, size_t total_nnz, int max_dim) {
+  SharedLayout S;
+  size_t o = align_up(base, 256);
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  S.zero_sort = o;
+  S.bucket = take(bucket_scratch_words(nc, total_tiles, kRadixBins, kMaxPasses) * sizeof(uint32_t));
+  S.run_status = take((total_tiles + (size_t)nc + 1) * sizeof(uint32_t));
+  S.run_ticket = take(64);
+  S.zero_sort_bytes = o - S.zero_sort;
+  S.item_cap = (int)(total_nnz / 8 + 4 * (size_t)nc + 64);
+  S.part_cap = (int)(total_nnz / 128 + 4 * (size_t)nc + 64);
+  S.part_stride = (max_dim + 3) / 4 * 4;
+  S.zero_apply = o;
+  S.long_count = take(64);
+  S.tickets = take((size_t)S.part_cap * sizeof(int32_t));
+  S.zero_apply_bytes = o - S.zero_apply;
+  S.items = take((size_t)S.item_cap * sizeof(LongItem));
+  S.part = take((size_t)S.part_cap * S.part_stride * sizeof(float));
+  S.end = o;
+  return S;
+}
+
+template <int V, int OPT, int MODE, bool FAST>
+static int launch_apply(const UpdParams& U, int max_short_ctas, cudaStream_t stream) {
+  const int sms = device_sm_count();
+  {
+    int per_sm = 0;
+    HB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &per_sm, update_short_kernel<V, OPT, MODE, FAST>, kUpdThreads, 0));
+    int grid = sms * (per_sm > 0 ? per_sm : 1);
+    if (grid > max_short_ctas) grid = max_short_ctas;
+    if (grid < 1) grid = 1;
     KernelScope ks(HB_K_SPARSE_UPDATE, stream);
-    sparse_update_kernel<V, OPT><<<P.total_ctas, kUpdThreads, smem, stream>>>(P);
+    update_short_kernel<V, OPT, MODE, FAST><<<grid, kUpdThreads, 0, stream>>>(U);
+    HB_CUDA_OK(cudaGetLastError());
   }
-  HB_CUDA_OK(cudaGetLastError());
-  if (X.total_ctas > 0) {
-    KernelScope ks(HB_K_SPARSE_FIXUP, stream);
-    sparse_update_fixup_kernel<V, OPT><<<X.total_ctas, kUpdThreads, 0, stream>>>(X);
+  {
+    int per_sm = 0;
+    HB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &per_sm, update_long_kernel<V, OPT, MODE, FAST>, kUpdThreads, 0));
+    int grid = sms * (per_sm > 0 ? per_sm : 1);
+    const int need = (U.item_cap + kUpdThreads / 32 - 1) / (kUpdThreads / 32);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    KernelScope ks(HB_K_UPDATE_LONG, stream);
+    update_long_kernel<V, OPT, MODE, FAST><<<grid, kUpdThreads, 0, stream>>>(U);
+    HB_CUDA_OK(cudaGetLastError());
   }
-  HB_CUDA_OK(cudaGetLastError());
   return HB_OK;
 }
 
-template <int V>
-static int launch_update(const UpdParams& P, const UpdParams& X, cudaStream_t stream) {
-  switch (P.opt) {
-    case HB_OPT_ADAGRAD: return launch_update_opt<V, HB_OPT_ADAGRAD>(P, X, stream);
-    case HB_OPT_LAZY_ADAM: return launch_update_opt<V, HB_OPT_LAZY_ADAM>(P, X, stream);
-    default: return launch_update_opt<V, HB_OPT_SGD>(P, X, stream);
+template <int V, int MODE>
+static int launch_apply_opt(const UpdParams& U, int max_short_ctas, cudaStream_t stream) {
+  if (MODE == kModeEmit) return launch_apply<V, HB_OPT_SGD, MODE, false>(U, max_short_ctas, stream);
+  switch (U.opt) {
+    case HB_OPT_ADAGRAD:
+      return U.fast ? launch_apply<V, HB_OPT_ADAGRAD, MODE, true>(U, max_short_ctas, stream)
+                    : launch_apply<V, HB_OPT_ADAGRAD, MODE, false>(U, max_short_ctas, stream);
+    case HB_OPT_LAZY_ADAM:
+      return U.fast ? launch_apply<V, HB_OPT_LAZY_ADAM, MODE, true>(U, max_short_ctas, stream)
+                    : launch_apply<V, HB_OPT_LAZY_ADAM, MODE, false>(U, max_short_ctas, stream);
+    default:
+      return launch_apply<V, HB_OPT_SGD, MODE, false>(U, max_short_ctas, stream);
   }
 }
 
-enum { kPhaseSort = 1, kPhaseApply = 2 };
+static int launch_apply_v(int V, bool emit, const UpdParams& U, int max_short_ctas, cudaStream_t stream) {
+  if (emit) {
+    switch (V) {
+      case 1: return launch_apply_opt<1, kModeEmit>(U, max_short_ctas, stream);
+      case 2: return launch_apply_opt<2, kModeEmit>(U, max_short_ctas, stream);
+      case 4: return launch_apply_opt<4, kModeEmit>(U, max_short_ctas, stream);
+      default: return launch_apply_opt<8, kModeEmit>(U, max_short_ctas, stream);
+    }
+  }
+  switch (V) {
+    case 1: return launch_apply_opt<1, kModeApply>(U, max_short_ctas, stream);
+    case 2: return launch_apply_opt<2, kModeApply>(U, max_short_ctas, stream);
+    case 4: return launch_apply_opt<4, kModeApply>(U, max_short_ctas, stream);
+    default: return launch_apply_opt<8, kModeApply>(U, max_short_ctas, stream);
+  }
+}
 
-static int validate_upd(int k, const hbUpdateFeature& f, const hbOptimizer* opt, int phases) {
+static int validate_upd(int k, const hbUpdateFeature& f, const hbOptimizer* opt, int phases,
+                        const UpdExtra* ex, bool emit) {
   HB_REQUIRE(f.dim >= 4 && f.dim % 4 == 0 && f.dim <= 1024,
              "update: feature %d dim %d must be a multiple of 4 in [4,1024]", k, f.dim);
-  HB_REQUIRE(f.nnz >= 0 && f.nnz <= INT32_MAX && f.nbags >= 0 && f.nbags <= INT32_MAX,
+  HB_REQUIRE(f.nnz >= 0 && f.nnz <= INT32_MAX / 2 && f.nbags >= 0 && f.nbags <= INT32_MAX,
              "update: feature %d bad nnz/nbags", k);
   HB_REQUIRE(f.offsets != nullptr || f.nnz == f.nbags,
              "update: feature %d has no offsets, so nnz must equal nbags", k);
-  HB_REQUIRE(f.rows >= 0 && f.rows < ((int64_t)1 << 32) - 1, "update: feature %d rows out of range", k);
+  HB_REQUIRE(f.rows >= 0 && f.rows < ((int64_t)1 << 32) - 2, "update: feature %d rows out of range", k);
   HB_REQUIRE(f.id_div >= 1, "update: feature %d id_div must be >= 1", k);
   HB_REQUIRE(f.grad_stride >= f.dim && f.grad_stride % 4 == 0,
              "update: feature %d grad_stride must be a multiple of 4 and >= dim", k);
   HB_REQUIRE(f.combiner >= HB_SUM && f.combiner <= HB_SQRTN, "update: feature %d bad combiner", k);
-  if (f.nnz > 0 && (phases & kPhaseSort)) HB_REQUIRE(f.ids != nullptr, "update: feature %d null ids", k);
+  if (f.nnz > 0 && (phases & kPhaseSort))
+    HB_REQUIRE(f.ids != nullptr || (ex && ex->keys32 != nullptr), "update: feature %d null ids", k);
   if (f.nnz > 0 && (phases & kPhaseApply)) {
-    HB_REQUIRE(f.table && f.grad, "update: feature %d null pointer", k);
-    HB_REQUIRE(((uintptr_t)f.table & 15) == 0 && ((uintptr_t)f.grad & 15) == 0,
-               "update: feature %d table/grad must be 16-byte aligned", k);
-    if (opt->kind == HB_OPT_ADAGRAD)
-      HB_REQUIRE(f.slot0 != nullptr, "update: feature %d Adagrad needs slot0 (accumulator)", k);
-    if (opt->kind == HB_OPT_LAZY_ADAM)
-      HB_REQUIRE(f.slot0 != nullptr && f.slot1 != nullptr, "update: feature %d LazyAdam needs slot0/slot1", k);
+    HB_REQUIRE(f.grad && ((uintptr_t)f.grad & 15) == 0, "update: feature %d grad must be non-null and 16-byte aligned", k);
+    if (!emit) {
+      HB_REQUIRE(f.table && ((uintptr_t)f.table & 15) == 0, "update: feature %d table must be non-null and 16-byte aligned", k);
+      if (opt->kind == HB_OPT_ADAGRAD)
+        HB_REQUIRE(f.slot0 != nullptr, "update: feature %d Adagrad needs slot0 (accumulator)", k);
+      if (opt->kind == HB_OPT_LAZY_ADAM)
+        HB_REQUIRE(f.slot0 != nullptr && f.slot1 != nullptr, "update: feature %d LazyAdam needs slot0/slot1", k);
+    }
   }
   return HB_OK;
 }
 
-// Sort (row, bag) pairs of every feature and run the fused update.  `id_div`
-// is shared by the features of one call (1 locally, W on a row-interleaved shard).
+// number of 9-bit digit positions a key space of `space` values needs; +2 keeps the
+// two sentinels (invalid id, padding) strictly above every valid key in the covered
+// bits, so they sort behind all real rows and never split a run
+static int radix_passes(int64_t space) {
+  const int bits = ilog2c(space + 2);
+  int p = (bits + kRadixBits - 1) / kRadixBits;
+  return p < 1 ? 1 : p;
+}
+
+size_t sparse_update_workspace_bytes(int n, const hbUpdateFeature* feats) {
+  size_t o = 0, max_shared = 0;
+  for (int c0 = 0; c0 < n; c0 += kMaxUpdFeats) {
+    const int nc = (n - c0 < kMaxUpdFeats) ? n - c0 : kMaxUpdFeats;
+    size_t tiles = 0, nnz = 0;
+    int max_dim = 4;
+    for (int k = 0; k < nc; ++k) {
+      const hbUpdateFeature& f = feats[c0 + k];
+      o = upd_layout(f, o).end;
+      tiles += bucket_tiles(f.nnz);
+      nnz += (size_t)f.nnz;
+      if (f.dim > max_dim) max_dim = f.dim;
+    }
+    const size_t sb = shared_layout(0, nc, tiles, nnz, max_dim).end;
+    if (sb > max_shared) max_shared = sb;
+  }
+  return align_up(o, 256) + max_shared + 256;
+}
+
+// Sort (row key, bag) pairs of every feature, find the runs and run the fused
+// duplicate-sum + sink.  `id_div` is shared by the features of one call.
 int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* opt, void* ws,
-                      size_t ws_bytes, int32_t* d_status, cudaStream_t stream,
-                      const WaitSpec* wait, const int32_t* const* n_dev, int phases) {
-  static const hbOptimizer kNoOpt = {HB_OPT_SGD, 0.f, 0.f, 0.f, 0.f, 1};
-  if (!(phases & kPhaseApply) && opt == nullptr) opt = &kNoOpt;
+                      size_t ws_bytes, int32_t* d_status, cudaStream_t stream, const WaitSpec* wait,
+                      const UpdExtra* extras, const EmitCtx* emit, int phases, UpdViews* views) {
+  static const hbOptimizer kNoOpt = {HB_OPT_SGD, 0.f, 0.f, 0.f, 0.f, 0, 1};
+  const bool is_emit = emit != nullptr;
+  if ((!(phases & kPhaseApply) || is_emit) && opt == nullptr) opt = &kNoOpt;
   HB_REQUIRE(n >= 1 && feats && opt, "update: bad arguments");
   HB_REQUIRE(opt->kind >= HB_OPT_SGD && opt->kind <= HB_OPT_LAZY_ADAM, "update: bad optimizer kind %d", opt->kind);
   for (int k = 0; k < n; ++k) {
-    int rc = validate_upd(k, feats[k], opt, phases);
+    int rc = validate_upd(k, feats[k], opt, phases, extras ? &extras[k] : nullptr, is_emit);
     if (rc != HB_OK) return rc;
     HB_REQUIRE(feats[k].id_div == feats[0].id_div, "update: all features of a call must share id_div");
+    if (extras) HB_REQUIRE(extras[k].key_kind == extras[0].key_kind, "update: all features of a call must share the key kind");
   }
-  size_t need = 0;
-  int rc = hbGroupSparseUpdateWorkspaceBytes(n, feats, &need);
-  if (rc != HB_OK) return rc;
+  const size_t need = sparse_update_workspace_bytes(n, feats);
   if (ws_bytes < need || (need > 0 && ws == nullptr)) {
     set_last_error("update: workspace %zu < required %zu bytes", ws_bytes, need);
     return HB_ERR_WORKSPACE;
   }
   unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+  const int key_kind = extras ? extras[0].key_kind : 0;
+  size_t feat_end = 0;
+  for (int k = 0; k < n; ++k) feat_end = upd_layout(feats[k], feat_end).end;
+  int rc = HB_OK;
 
+  size_t off = 0;
   for (int c0 = 0; c0 < n; c0 += kMaxUpdFeats) {
     const int nc = (n - c0 < kMaxUpdFeats) ? n - c0 : kMaxUpdFeats;
-    // layouts
     UpdLayout L[kMaxUpdFeats];
-    size_t off = 0;
-    {
-      // recompute the running offset of this chunk
-      for (int k = 0; k < c0; ++k) off = upd_layout(feats[k], off).end;
-    }
+    int passes[kMaxUpdFeats];
     size_t o = off;
-    int total_tiles = 0, max_passes = 0;
+    size_t total_tiles = 0, total_nnz = 0;
+    int max_passes = 0, max_dim = 4;
     for (int k = 0; k < nc; ++k) {
-      L[k] = upd_layout(feats[c0 + k], o);
+      const hbUpdateFeature& f = feats[c0 + k];
+      const UpdExtra* ex = extras ? &extras[c0 + k] : nullptr;
+      L[k] = upd_layout(f, o);
       o = L[k].end;
-      total_tiles += bucket_tiles(feats[c0 + k].nnz);
-      if (feats[c0 + k].nnz > 0 && L[k].passes > max_passes) max_passes = L[k].passes;
+      total_tiles += (size_t)bucket_tiles(f.nnz);
+      total_nnz += (size_t)f.nnz;
+      if (f.dim > max_dim) max_dim = f.dim;
+      int64_t space = f.rows;
+      if (ex && ex->key_kind == 1) space = (int64_t)feats[0].id_div << ex->lbits;
+      passes[k] = radix_passes(space);
+      HB_REQUIRE(passes[k] <= kMaxPasses, "update: feature %d key space needs more than %d radix passes", c0 + k, kMaxPasses);
+      if (f.nnz > 0 && passes[k] > max_passes) max_passes = passes[k];
+      if (views) {
+        views[c0 + k].ukey = reinterpret_cast<const uint32_t*>(base + L[k].ukey);
+        views[c0 + k].ustart = reinterpret_cast<const int32_t*>(base + L[k].ustart);
+        views[c0 + k].counts = reinterpret_cast<const int32_t*>(base + L[k].counts);
+      }
     }
-    int32_t* counts = reinterpret_cast<int32_t*>(base + o);  // chunk-shared radix counters
+    off = o;
+    const SharedLayout S = shared_layout(feat_end, nc, total_tiles, total_nnz, max_dim);
 
-    // 1. bag map for CSR features
     if (phases & kPhaseSort) {
+      // 1. bag map for CSR features
       BagMapParams B;
       B.status = d_status;
       B.nfeats = 0;
@@ -702,79 +952,128 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         bag_of_position_kernel<<<ctas, 256, 0, stream>>>(B);
         HB_CUDA_OK(cudaGetLastError());
       }
-    }
 
-    // 2. LSD radix sort: one memset, one histogram kernel over the ids (all digit
-    //    positions), then one kernel per digit position; feature k takes part in
-    //    pass p iff p < passes[k]
-    if (max_passes > 0 && (phases & kPhaseSort)) {
-      const size_t words = bucket_scratch_words(nc, (size_t)total_tiles, kRadixBins, max_passes);
-      HB_CUDA_OK(cudaMemsetAsync(counts, 0, words * sizeof(uint32_t), stream));
-      BucketScratch sc = bucket_scratch_carve(reinterpret_cast<uint32_t*>(counts), nc,
-                                              (size_t)total_tiles, kRadixBins, max_passes);
-      for (int p = -1; p < max_passes; ++p) {  // p == -1: histogram launch
-        BucketParams bp;
-        bp.nsegs = 0;
-        int tiles = 0;
-        for (int k = 0; k < nc; ++k) {
-          const hbUpdateFeature& f = feats[c0 + k];
-          if (f.nnz == 0 || (p >= 0 && p >= L[k].passes)) continue;
-          BucketSeg& s = bp.seg[bp.nsegs++];
-          uint32_t* kA = reinterpret_cast<uint32_t*>(base + L[k].keysA);
-          uint32_t* kB = reinterpret_cast<uint32_t*>(base + L[k].keysB);
-          int32_t* vA = reinterpret_cast<int32_t*>(base + L[k].valsA);
-          int32_t* vB = reinterpret_cast<int32_t*>(base + L[k].valsB);
-          if (p <= 0) {
-            s.in_keys = f.ids;
-            s.in_vals = f.offsets ? reinterpret_cast<int32_t*>(base + L[k].bagmap) : nullptr;
-            s.out_keys = kA;
-            s.out_vals = vA;
-          } else {
-            const bool a2b = (p & 1) == 1;  // pass 1: A->B, pass 2: B->A, ...
-            s.in_keys = a2b ? kA : kB;
-            s.in_vals = a2b ? vA : vB;
-            s.out_keys = a2b ? kB : kA;
-            s.out_vals = a2b ? vB : vA;
+      // 2. LSD radix sort: one memset, one histogram kernel over the inputs (all
+      //    digit positions), then one kernel per digit position; feature k takes
+      //    part in pass p iff p < passes[k]
+      HB_CUDA_OK(cudaMemsetAsync(base + S.zero_sort, 0, S.zero_sort_bytes, stream));
+      if (max_passes > 0) {
+        BucketScratch sc = bucket_scratch_carve(reinterpret_cast<uint32_t*>(base + S.bucket), nc,
+                                                total_tiles, kRadixBins, max_passes);
+        for (int p = -1; p < max_passes; ++p) {  // p == -1: histogram launch
+          BucketParams bp;
+          bp.nsegs = 0;
+          int tiles = 0;
+          for (int k = 0; k < nc; ++k) {
+            const hbUpdateFeature& f = feats[c0 + k];
+            const UpdExtra* ex = extras ? &extras[c0 + k] : nullptr;
+            if (f.nnz == 0 || (p >= 0 && p >= passes[k])) continue;
+            BucketSeg& s = bp.seg[bp.nsegs++];
+            uint32_t* kA = reinterpret_cast<uint32_t*>(base + L[k].keysA);
+            uint32_t* kB = reinterpret_cast<uint32_t*>(base + L[k].keysB);
+            int32_t* vA = reinterpret_cast<int32_t*>(base + L[k].valsA);
+            int32_t* vB = reinterpret_cast<int32_t*>(base + L[k].valsB);
+            if (p <= 0) {
+              s.in_keys = (key_kind == 2) ? (const void*)ex->keys32 : (const void*)f.ids;
+              s.in_vals = f.offsets ? reinterpret_cast<int32_t*>(base + L[k].bagmap) : nullptr;
+              // the requester-side sort carries POSITIONS (the inverse map needs them);
+              // bags are looked up from positions afterwards
+              if (ex && ex->inv != nullptr) s.in_vals = nullptr;
+              s.out_keys = kA;
+              s.out_vals = vA;
+            } else {
+              const bool a2b = (p & 1) == 1;  // pass 1: A->B, pass 2: B->A, ...
+              s.in_keys = a2b ? kA : kB;
+              s.in_vals = a2b ? vA : vB;
+              s.out_keys = a2b ? kB : kA;
+              s.out_vals = a2b ? vB : vA;
+            }
+            s.out_inv = nullptr;
+            s.out_sizes = nullptr;
+            s.n = (int32_t)f.nnz;
+            s.n_dev = ex ? ex->n_dev : nullptr;
+            s.tile_begin = tiles;
+            s.shift = (p < 0 ? 0 : p) * kRadixBits;
+            s.key_limit = (uint32_t)f.rows;
+            s.hist_slot = k;
+            s.passes = passes[k];
+            s.lbits = ex ? ex->lbits : 0;
+            tiles += bucket_tiles(f.nnz);
           }
-          s.out_inv = nullptr;
-          s.out_sizes = nullptr;
-          s.n = (int32_t)f.nnz;
-          s.n_dev = n_dev ? n_dev[c0 + k] : nullptr;
-          s.tile_begin = tiles;
-          s.shift = (p < 0 ? 0 : p) * kRadixBits;
-          s.key_limit = (uint32_t)f.rows;
-          s.hist_slot = k;
-          s.passes = L[k].passes;
-          tiles += bucket_tiles(f.nnz);
+          if (bp.nsegs == 0) break;
+          bp.hist = sc.hist;
+          bp.status = sc.status[p < 0 ? 0 : p];
+          bp.ticket = sc.ticket[p < 0 ? 0 : p];
+          bp.nbins = kRadixBins;
+          bp.total_tiles = tiles;
+          bp.npass = max_passes;
+          bp.pass = p < 0 ? 0 : p;
+          bp.digit_bits = kRadixBits;
+          bp.p = (key_kind == 1) ? (int32_t)feats[0].id_div : 1;
+          bp.m = 1; bp.pow2_mask = 0;
+          bp.div = feats[0].id_div;
+          bp.div_shift = ((bp.div & (bp.div - 1)) == 0 && bp.div <= (1 << 30)) ? ilog2c(bp.div) : -1;
+          if (p > 0) rc = bucket_pass_launch<RadixNextTraits>(bp, stream, HB_K_SORT_PASS);
+          else if (key_kind == 1)
+            rc = p < 0 ? bucket_hist_launch<RadixCompositeTraits>(bp, stream, HB_K_SORT_HIST)
+                       : bucket_pass_launch<RadixCompositeTraits>(bp, stream, HB_K_SORT_PASS);
+          else if (key_kind == 2)
+            rc = p < 0 ? bucket_hist_launch<RadixDirectTraits>(bp, stream, HB_K_SORT_HIST)
+                       : bucket_pass_launch<RadixDirectTraits>(bp, stream, HB_K_SORT_PASS);
+          else
+            rc = p < 0 ? bucket_hist_launch<RadixFirstTraits>(bp, stream, HB_K_SORT_HIST)
+                       : bucket_pass_launch<RadixFirstTraits>(bp, stream, HB_K_SORT_PASS);
+          if (rc != HB_OK) return rc;
         }
-        if (bp.nsegs == 0) break;
-        bp.hist = sc.hist;
-        bp.status = sc.status[p < 0 ? 0 : p];
-        bp.ticket = sc.ticket[p < 0 ? 0 : p];
-        bp.nbins = kRadixBins;
-        bp.total_tiles = tiles;
-        bp.npass = max_passes;
-        bp.pass = p < 0 ? 0 : p;
-        bp.digit_bits = kRadixBits;
-        bp.p = 1; bp.m = 1; bp.pow2_mask = 0;
-        bp.div = feats[0].id_div;
-        bp.div_shift = ((bp.div & (bp.div - 1)) == 0 && bp.div <= (1 << 30)) ? ilog2c(bp.div) : -1;
-        if (p < 0) rc = bucket_hist_launch<RadixFirstTraits>(bp, stream, HB_K_SORT_HIST);
-        else if (p == 0) rc = bucket_pass_launch<RadixFirstTraits>(bp, stream, HB_K_SORT_PASS);
-        else rc = bucket_pass_launch<RadixNextTraits>(bp, stream, HB_K_SORT_PASS);
-        if (rc != HB_OK) return rc;
       }
+
+      // 3. runs
+      RunParams R;
+      R.status = reinterpret_cast<uint32_t*>(base + S.run_status);
+      R.ticket = reinterpret_cast<uint32_t*>(base + S.run_ticket);
+      R.d_status = d_status;
+      R.nfeats = nc;
+      size_t static_tiles = 0;
+      for (int k = 0; k < nc; ++k) {
+        const hbUpdateFeature& f = feats[c0 + k];
+        const UpdExtra* ex = extras ? &extras[c0 + k] : nullptr;
+        const bool inA = (passes[k] & 1) == 1;  // 1 pass -> A, 2 -> B, 3 -> A, ...
+        RunFeat& F = R.f[k];
+        F.keys = reinterpret_cast<uint32_t*>(base + (inA ? L[k].keysA : L[k].keysB));
+        F.vals = reinterpret_cast<int32_t*>(base + (inA ? L[k].valsA : L[k].valsB));
+        F.ukey = reinterpret_cast<uint32_t*>(base + L[k].ukey);
+        F.ustart = reinterpret_cast<int32_t*>(base + L[k].ustart);
+        F.counts = reinterpret_cast<int32_t*>(base + L[k].counts);
+        F.inv = ex ? ex->inv : nullptr;
+        F.owner_start1 = ex ? ex->owner_start1 : nullptr;
+        F.n_dev = ex ? ex->n_dev : nullptr;
+        F.n = (int32_t)f.nnz;
+        F.lbits = ex ? ex->lbits : 0;
+        static_tiles += (size_t)((f.nnz + kRunTile - 1) / kRunTile) + 1;
+      }
+      const int maxg = device_sm_count() * 4;
+      const int grid = static_tiles < (size_t)maxg ? (int)static_tiles : maxg;
+      KernelScope ks(HB_K_RUNS, stream);
+      runs_kernel<<<grid, kUpdThreads, 0, stream>>>(R);
+      HB_CUDA_OK(cudaGetLastError());
     }
 
-    // 3./4. fused update + fix-up, one launch per V
+    // 4./5. fused duplicate-sum + sink, one launch pair per V class
     if (!(phases & kPhaseApply)) continue;
     for (int V = 1; V <= 8; V <<= 1) {
       UpdParams U;
       U.wait = wait ? *wait : WaitSpec{nullptr, 0, 0};
+      if (is_emit) U.emit = *emit;
+      else { for (int i = 0; i < kMaxWorld; ++i) U.emit.peers.p[i] = nullptr; U.emit.window_off = 0; U.emit.world = 1; }
       U.status = d_status;
+      U.long_count = reinterpret_cast<int32_t*>(base + S.long_count);
+      U.items = reinterpret_cast<LongItem*>(base + S.items);
+      U.part = reinterpret_cast<float*>(base + S.part);
+      U.tickets = reinterpret_cast<int32_t*>(base + S.tickets);
+      U.item_cap = S.item_cap; U.part_cap = S.part_cap; U.part_stride = S.part_stride;
       U.nfeats = 0;
-      U.total_ctas = 0;
       U.opt = opt->kind;
+      U.fast = (opt->flags & HB_OPT_FLAG_FAST_MATH) ? 1 : 0;
       U.lr = opt->lr;
       U.beta1 = opt->beta1; U.beta2 = opt->beta2; U.eps = opt->eps;
       U.omb1 = 1.0f - opt->beta1; U.omb2 = 1.0f - opt->beta2;
@@ -783,43 +1082,38 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         U.lr = (float)((double)opt->lr * sqrt(1.0 - pow((double)opt->beta2, t)) /
                        (1.0 - pow((double)opt->beta1, t)));
       }
-      int fix_ctas = 0;
-      int fix_begin[kMaxUpdFeats];
+      int max_ctas = 0;
       for (int k = 0; k < nc; ++k) {
         const hbUpdateFeature& f = feats[c0 + k];
+        const UpdExtra* ex = extras ? &extras[c0 + k] : nullptr;
         if (L[k].V != V || f.nnz == 0) continue;
         UpdFeat& F = U.f[U.nfeats];
-        const bool inA = (L[k].passes & 1) == 1;  // 1 pass -> A, 2 -> B, 3 -> A, ...
+        const bool inA = (passes[k] & 1) == 1;
         F.table = f.table; F.slot0 = f.slot0; F.slot1 = f.slot1;
         F.grad = f.grad; F.offsets = f.offsets;
-        F.keys = reinterpret_cast<uint32_t*>(base + (inA ? L[k].keysA : L[k].keysB));
-        F.bags = reinterpret_cast<int32_t*>(base + (inA ? L[k].valsA : L[k].valsB));
-        F.st_part = reinterpret_cast<float*>(base + L[k].st_part);
-        F.st_key = reinterpret_cast<uint32_t*>(base + L[k].st_key);
-        F.st_flag = reinterpret_cast<int32_t*>(base + L[k].st_flag);
-        F.n_dev = n_dev ? n_dev[c0 + k] : nullptr;
+        F.ukey = reinterpret_cast<uint32_t*>(base + L[k].ukey);
+        F.ustart = reinterpret_cast<int32_t*>(base + L[k].ustart);
+        F.counts = reinterpret_cast<int32_t*>(base + L[k].counts);
+        F.vals = reinterpret_cast<int32_t*>(base + (inA ? L[k].valsA : L[k].valsB));
+        F.pos2bag = (ex && ex->inv != nullptr && f.offsets != nullptr)
+                        ? reinterpret_cast<const int32_t*>(base + L[k].bagmap) : nullptr;
+        F.emit_send_off = ex ? ex->emit_send_off : nullptr;
+        F.emit_remote_base = ex ? ex->emit_remote_base : nullptr;
+        F.emit_off = ex ? ex->emit_off : 0;
+        F.emit_cap = ex ? ex->emit_cap : 0;
         F.rows = f.rows; F.grad_stride = f.grad_stride;
-        F.n = (int32_t)f.nnz; F.dim = f.dim; F.combiner = f.combiner;
+        F.dim = f.dim; F.combiner = f.combiner;
         F.log2g = L[k].log2g;
-        F.cta_begin = U.total_ctas;
-        F.nst = L[k].nst;
-        U.total_ctas += L[k].nst;
-        fix_begin[U.nfeats] = fix_ctas;
-        fix_ctas += (L[k].nst + (kUpdThreads / 32) - 1) / (kUpdThreads / 32);
+        const int uc = (kUpdThreads >> L[k].log2g) * kNU;
+        F.max_chunks = (int)((f.nnz + uc - 1) / uc);
+        max_ctas += F.max_chunks;
         U.nfeats++;
       }
       if (U.nfeats == 0) continue;
-      // fix-up launch: same params, cta_begin re-based to fix-up CTAs
-      UpdParams X = U;
-      for (int k = 0; k < X.nfeats; ++k) X.f[k].cta_begin = fix_begin[k];
-      X.total_ctas = fix_ctas;
-      switch (V) {
-        case 1: rc = launch_update<1>(U, X, stream); break;
-        case 2: rc = launch_update<2>(U, X, stream); break;
-        case 4: rc = launch_update<4>(U, X, stream); break;
-        default: rc = launch_update<8>(U, X, stream); break;
-      }
+      HB_CUDA_OK(cudaMemsetAsync(base + S.zero_apply, 0, S.zero_apply_bytes, stream));
+      rc = launch_apply_v(V, is_emit, U, max_ctas, stream);
       if (rc != HB_OK) return rc;
+      wait = nullptr;  // later launches are stream-ordered behind the first
     }
   }
   return HB_OK;
@@ -832,22 +1126,11 @@ extern "C" {
 int hbGroupSparseUpdateWorkspaceBytes(int n, const hbUpdateFeature* feats, size_t* bytes) {
   using namespace hb;
   HB_REQUIRE(n >= 1 && feats && bytes, "hbGroupSparseUpdateWorkspaceBytes: bad argument");
-  size_t o = 0;
-  size_t max_chunk_counts = 0;
-  for (int c0 = 0; c0 < n; c0 += kMaxUpdFeats) {
-    const int nc = (n - c0 < kMaxUpdFeats) ? n - c0 : kMaxUpdFeats;
-    size_t tiles = 0;
-    for (int k = 0; k < nc; ++k) {
-      const hbUpdateFeature& f = feats[c0 + k];
-      HB_REQUIRE(f.nnz >= 0 && f.nnz <= INT32_MAX && f.dim >= 4 && f.dim % 4 == 0 && f.dim <= 1024,
-                 "hbGroupSparseUpdateWorkspaceBytes: feature %d bad nnz/dim", c0 + k);
-      o = upd_layout(f, o).end;
-      tiles += bucket_tiles(f.nnz);
-    }
-    const size_t cb = align_up(bucket_scratch_words(nc, tiles, kRadixBins, kMaxPasses) * sizeof(uint32_t), 256);
-    if (cb > max_chunk_counts) max_chunk_counts = cb;
-  }
-  *bytes = o + max_chunk_counts + 256;
+  for (int k = 0; k < n; ++k)
+    HB_REQUIRE(feats[k].nnz >= 0 && feats[k].nnz <= INT32_MAX / 2 && feats[k].dim >= 4 &&
+                   feats[k].dim % 4 == 0 && feats[k].dim <= 1024,
+               "hbGroupSparseUpdateWorkspaceBytes: feature %d bad nnz/dim", k);
+  *bytes = sparse_update_workspace_bytes(n, feats);
   return HB_OK;
 }
 
@@ -855,19 +1138,20 @@ int hbGroupLookupBackwardUpdate(int n, const hbUpdateFeature* feats, const hbOpt
                                 void* d_workspace, size_t workspace_bytes, int32_t* d_status,
                                 hbStream stream) {
   return hb::sparse_update_run(n, feats, opt, d_workspace, workspace_bytes, d_status,
-                               (cudaStream_t)stream, nullptr, nullptr, hb::kPhaseSort | hb::kPhaseApply);
+                               (cudaStream_t)stream, nullptr, nullptr, nullptr,
+                               hb::kPhaseSort | hb::kPhaseApply, nullptr);
 }
 
 int hbGroupSparseSort(int n, const hbUpdateFeature* feats, void* d_workspace, size_t workspace_bytes,
                       int32_t* d_status, hbStream stream) {
   return hb::sparse_update_run(n, feats, nullptr, d_workspace, workspace_bytes, d_status,
-                               (cudaStream_t)stream, nullptr, nullptr, hb::kPhaseSort);
+                               (cudaStream_t)stream, nullptr, nullptr, nullptr, hb::kPhaseSort, nullptr);
 }
 
 int hbGroupSparseApply(int n, const hbUpdateFeature* feats, const hbOptimizer* opt, void* d_workspace,
                        size_t workspace_bytes, int32_t* d_status, hbStream stream) {
   return hb::sparse_update_run(n, feats, opt, d_workspace, workspace_bytes, d_status,
-                               (cudaStream_t)stream, nullptr, nullptr, hb::kPhaseApply);
+                               (cudaStream_t)stream, nullptr, nullptr, nullptr, hb::kPhaseApply, nullptr);
 }
 
 }  // extern "C"

@@ -17,6 +17,42 @@ from hybridbackend_b200 import _lib
 from hybridbackend_b200 import _util
 
 
+class _AlltoallFn(torch.autograd.Function):
+  """alltoall_fn of collective.py:302-319: the gradient of an equal-split
+  alltoall is the alltoall of the upstream gradient."""
+
+  @staticmethod
+  def forward(ctx, coll, value):
+    ctx.coll = coll
+    return coll._alltoall_equal([value.detach()])[0]
+
+  @staticmethod
+  def backward(ctx, grad):
+    return None, ctx.coll._alltoall_equal([grad.contiguous()])[0]
+
+
+class _AlltoallvFn(torch.autograd.Function):
+  """alltoallv_fn of collective.py:324-348: the gradient of
+  alltoall(value, sizes) is the alltoallv of the (dense) upstream gradient with
+  the RECEIVED sizes, so every row's gradient returns to the rank it came from."""
+
+  @staticmethod
+  def forward(ctx, coll, value, sizes, common_shape):
+    outs, osz = coll._alltoallv_n([value.detach()], [sizes],
+                                  None if common_shape is None else [common_shape])
+    ctx.coll, ctx.common_shape = coll, common_shape
+    ctx.save_for_backward(osz[0])
+    ctx.mark_non_differentiable(osz[0])
+    return outs[0], osz[0]
+
+  @staticmethod
+  def backward(ctx, grad, _sizes_grad):
+    (osz,) = ctx.saved_tensors
+    outs, _ = ctx.coll._alltoallv_n([grad.contiguous()], [osz],
+                                    None if ctx.common_shape is None else [ctx.common_shape])
+    return None, outs[0], None, None
+
+
 class Topology:
   ALL = 0
   INTRA_NODE = 1
@@ -27,14 +63,19 @@ class Collective:
   _instance = None
 
   def __init__(self, rank, world_size, local_size=None, window_bytes=64 << 20,
-               device=None, token_allgather=None):
+               device=None, token_allgather=None, _handle=None):
     self.rank, self.world_size = int(rank), int(world_size)
     self.local_size = int(local_size or world_size)
     self.device = torch.device(device if device is not None else
                                f'cuda:{torch.cuda.current_device()}')
     self._comm = C.c_void_p()
-    token = (C.c_ubyte * _lib.TOKEN_BYTES)()
+    self._h_sizes = None
     L = _lib.lib()
+    if _handle is not None:  # member of an in-process group (local_group)
+      self._comm = _handle
+      self.window_bytes = int(L.hbCommWindowBytes(self._comm))
+      return
+    token = (C.c_ubyte * _lib.TOKEN_BYTES)()
     with torch.cuda.device(self.device):
       _lib.check(L.hbCommCreate(self.rank, self.world_size, self.local_size,
                                 C.c_size_t(window_bytes), C.byref(self._comm), token),
@@ -49,7 +90,19 @@ class Collective:
         buf = (C.c_ubyte * len(all_tokens)).from_buffer_copy(all_tokens)
         _lib.check(L.hbCommConnect(self._comm, buf), 'Collective.connect')
     self.window_bytes = int(L.hbCommWindowBytes(self._comm))
-    self._h_sizes = None
+
+  @classmethod
+  def local_group(cls, world_size, window_bytes=64 << 20, device=None):
+    """world_size communicators on ONE device wired to each other in-process
+    (hbCommCreateLocalGroup): rank r must then be driven by its own host thread,
+    exactly as a process per GPU would drive it.  Lets a single-GPU box run the
+    multi-rank kernels (CI), or W logical shards share one GPU."""
+    dev = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+    handles = (C.c_void_p * world_size)()
+    with torch.cuda.device(dev):
+      _lib.check(_lib.lib().hbCommCreateLocalGroup(int(world_size), C.c_size_t(window_bytes), handles),
+                 'Collective.local_group')
+    return [cls(r, world_size, device=dev, _handle=C.c_void_p(handles[r])) for r in range(world_size)]
 
   # -- lifecycle ---------------------------------------------------------------
   @classmethod
@@ -74,9 +127,38 @@ class Collective:
   def handle(self):
     return self._comm
 
+  def _attach_status(self):
+    st = _util.status_word(self.device)
+    _lib.lib().hbCommSetStatusWord(self._comm, C.c_void_p(st.data_ptr()))
+    return st
+
   def barrier(self):
     with torch.cuda.device(self.device):
+      self._attach_status()
       _lib.check(_lib.lib().hbCommBarrier(self._comm, _util.stream_ptr()), 'barrier')
+
+  def allreduce(self, value, scale=1.0, out=None):
+    """Sum of `value` (float32) over the ranks, times `scale`; every rank adds the
+    contributions in rank order (bit-identical replicas).  The dense-gradient
+    path of replicated small tables (training/gradient.py:157-160; scale=1/W is
+    the mean of :77-97) -- W x the bytes of a ring all-reduce, sized for those."""
+    _util.require_cuda(value, 'allreduce: value')
+    if value.dtype != torch.float32:
+      raise TypeError('allreduce: float32 only')
+    if out is None:
+      out = torch.empty_like(value)
+    if self.world_size == 1:
+      out.copy_(value)
+      if scale != 1.0:
+        out.mul_(scale)
+      return out
+    with torch.cuda.device(self.device):
+      st = self._attach_status()
+      _lib.check(_lib.lib().hbAllreduceSumF32(
+          self._comm, C.c_void_p(value.data_ptr()), C.c_void_p(out.data_ptr()),
+          C.c_int64(value.numel()), C.c_float(scale), C.c_void_p(st.data_ptr()),
+          _util.stream_ptr()), 'allreduce')
+    return out
 
   # -- alltoall ------------------------------------------------------------------
   def _cast_n(self, tensors, to_dtype):
@@ -94,7 +176,7 @@ class Collective:
     return outs
 
   def alltoall(self, value, sizes=None, common_shape=None, topology=Topology.ALL,
-               name=None, wire_dtype=None):
+               name=None, wire_dtype=None, check=True):
     """Shuffle value partitions across devices (collective.py:271-350).
 
     sizes=None: equal split of dim 0 across ranks (HbNcclAlltoall); otherwise
@@ -104,10 +186,16 @@ class Collective:
     reference's `comm_wire_dtype` option, collective.py:291-296,
     nccl_alltoallv.cc:57-88)."""
     del name
+    self._check = check
     if topology != Topology.ALL:
       raise NotImplementedError('only Topology.ALL is built (single NVSwitch domain); '
                                 'INTRA/INTER_NODE belong to the multi-node path')
     single = isinstance(value, torch.Tensor)
+    if single and value.requires_grad and wire_dtype is None:
+      # differentiable form (collective.py:302-348)
+      if sizes is None:
+        return _AlltoallFn.apply(self, value)
+      return _AlltoallvFn.apply(self, value, sizes, common_shape)
     values = [value] if single else list(value)
     half_wire = (wire_dtype == torch.float16 and self.world_size > 1 and
                  all(v.dtype == torch.float32 for v in values))
@@ -158,6 +246,7 @@ class Collective:
     if self._h_sizes is None or self._h_sizes.numel() < n * W:
       self._h_sizes = torch.empty(max(n * W, 256), dtype=torch.int32).pin_memory()
     with torch.cuda.device(dev):
+      self._attach_status()
       _lib.check(L.hbAlltoallvNSizes(
           self._comm, n, _lib.ptr_array([s.data_ptr() for s in sizes]),
           _lib.ptr_array([r.data_ptr() for r in recv]), C.c_void_p(self._h_sizes.data_ptr()),
@@ -182,6 +271,18 @@ class Collective:
           _lib.i64_array(common), _lib.i32_array([v.element_size() for v in values]),
           _lib.ptr_array([o.data_ptr() for o in outs]), C.c_void_p(st.data_ptr()),
           _util.stream_ptr()), 'alltoallv')
+      if getattr(self, '_check', True):
+        # the host already blocked for the sizes (as the reference does); one more
+        # status read turns a receive-window overflow or a missing peer into an
+        # exception instead of uninitialised outputs
+        try:
+          _util.check_status(dev)
+        except RuntimeError as e:
+          if 'overflow' in str(e):
+            raise RuntimeError(
+                f'alltoall: a rank receives more than half of the free window '
+                f'({self.window_bytes} B); create the Collective with a larger window_bytes') from e
+          raise
     return outs, recv
 
 

@@ -30,7 +30,7 @@ def _feature_struct(weight, ids, offsets, nbags, out, out_stride, combiner, id_d
   return _lib.hbLookupFeature(
       weight.data_ptr(), weight.shape[0], ids.data_ptr(),
       offsets.data_ptr() if offsets is not None else None, nbags, out.data_ptr(),
-      out_stride, weight.shape[1], _lib.COMBINER[combiner], id_div)
+      out_stride, weight.shape[1], _lib.COMBINER[combiner], id_div, ids.numel())
 
 
 def _check_inputs(weight, ids, offsets, what):
@@ -114,6 +114,7 @@ class GroupLookup:
     self._upd_ws = None
     self._saved = None
     self._sharded = None
+    self._dense = {}  # replicated tables: dense gradient buffers and row ids
     world = collective.world_size if collective is not None else 1
     self.sharded_idx = [k for k, t in enumerate(self.tables)
                         if world > 1 and isinstance(t, ShardedEmbeddingWeights) and t.sharded]
@@ -146,7 +147,7 @@ class GroupLookup:
     L = _lib.lib()
     with torch.cuda.device(self.device):
       self._sort_done = None
-      if self.local_idx and prepare_backward and self.overlap_backward_sort and not self._needs_allgather():
+      if self.local_idx and prepare_backward and self.overlap_backward_sort:
         self._presort(ids, offsets, B, st)
       if self.local_idx:
         feats = (_lib.hbLookupFeature * len(self.local_idx))()
@@ -166,9 +167,15 @@ class GroupLookup:
       _util.check_status(self.device)
     return out
 
-  def _needs_allgather(self):
+  def _sync(self):
     return (self.collective is not None and self.collective.world_size > 1 and
             self.sync_replicated and bool(self.local_idx))
+
+  def close(self):
+    """Release the sharded plan (the Collective can then host another GroupLookup)."""
+    if self._sharded is not None:
+      self._sharded.close()
+      self._sharded = None
 
   def _update_feats(self, ids, offsets, B, grad=None, optimizer=None):
     m = len(self.local_idx)
@@ -270,29 +277,13 @@ class GroupLookup:
     st = _util.status_word(self.device)
     L = _lib.lib()
     with torch.cuda.device(self.device):
-      if self.local_idx:
-        m = len(self.local_idx)
-        feats = (_lib.hbUpdateFeature * m)()
-        sync = (self.collective is not None and self.collective.world_size > 1 and
-                self.sync_replicated)
-        keep = []
-        for j, k in enumerate(self.local_idx):
-          t = self.tables[k]
-          w = _weight_of(t)
-          slots = self._slots(k, optimizer)
-          ids_k, off_k, g_k, g_stride, nb = ids[k], offsets[k], grad[:, self.col_offsets[k]:], grad.stride(0), B
-          if sync:
-            ids_k, g_k, nb = self._allgather_replicated(k, ids[k], offsets[k], grad)
-            off_k, g_stride = None, g_k.stride(0)
-            keep.append((ids_k, g_k))
-          feats[j] = _lib.hbUpdateFeature(
-              w.data_ptr(), slots[0].data_ptr() if len(slots) > 0 else None,
-              slots[1].data_ptr() if len(slots) > 1 else None, w.shape[0],
-              ids_k.data_ptr(), off_k.data_ptr() if off_k is not None else None,
-              nb, ids_k.numel(), g_k.data_ptr(), g_stride,
-              w.shape[1], _lib.COMBINER[self.combiners[k]], 1)
+      if self.local_idx and self._sync():
+        self._replicated_dense_update(ids, offsets, B, grad, optimizer, desc, st)
+      elif self.local_idx:
+        feats = self._update_feats(ids, offsets, B, grad, optimizer)
+        m = len(feats)
         ws = self._workspace(feats)
-        if self._sort_done is not None and not sync:
+        if self._sort_done is not None:
           torch.cuda.current_stream().wait_event(self._sort_done)
           self._sort_done = None
           _lib.check(L.hbGroupSparseApply(
@@ -310,25 +301,69 @@ class GroupLookup:
     if check:
       _util.check_status(self.device)
 
-  def _allgather_replicated(self, k, ids_k, off_k, grad):
-    """Replicated ("small") tables: every rank applies the gradients of ALL ranks
-    so replicas stay identical -- the reference all-gathers the IndexedSlices
-    values+indices of replicated sparse gradients (training/gradient.py:163-177).
-    NCCL all-gather via torch.distributed: the dense/replicated path keeps NCCL
-    (SURVEY.md section 2 row 4)."""
-    import torch.distributed as dist  # pylint: disable=import-outside-toplevel
-    if off_k is not None:
-      raise NotImplementedError(
-          'gradient all-gather of a replicated table needs one id per bag; give multi-id '
-          'bags to sharded tables or pass sync_replicated=False')
+  def _replicated_dense_update(self, ids, offsets, B, grad, optimizer, desc, st):
+    """Replicated ("small") tables at world_size > 1, as the reference routes them
+    (training/gradient.py:132-141): the sparse gradient is DENSIFIED to [rows, dim]
+    (duplicates summed in position order), all-reduced over the ranks (:157-160),
+    multiplied by 1/W (_mean, :77-97 via :216) and applied as a dense gradient, i.e.
+    to every row.  Device work: (1) the fused sort + duplicate-sum kernels with
+    SGD(lr=-1) on a zeroed buffer produce the dense gradient exactly and
+    deterministically (0 - (-1*g) = g), (2) hbAllreduceSumF32 over the peer windows,
+    rank-order sum scaled by 1/W, (3) the same fused kernels apply the optimizer with
+    ids = 0..rows-1 (one entry per row = a dense apply)."""
+    L = _lib.lib()
     W = self.collective.world_size
-    d = self.dims[k]
-    g_local = grad[:, self.col_offsets[k]:self.col_offsets[k] + d].contiguous()
-    all_ids = torch.empty(W * ids_k.numel(), dtype=torch.int64, device=self.device)
-    all_g = torch.empty(W * g_local.shape[0], d, dtype=torch.float32, device=self.device)
-    dist.all_gather_into_tensor(all_ids, ids_k.contiguous())
-    dist.all_gather_into_tensor(all_g, g_local)
-    return all_ids, all_g, all_ids.numel()
+    m = len(self.local_idx)
+    key = (grad.dtype, grad.device)
+    if self._dense.get('key') != key:
+      total = sum(_weight_of(self.tables[k]).numel() for k in self.local_idx)
+      self._dense = {'key': key, 'flat': torch.empty(total, dtype=torch.float32, device=self.device),
+                     'rows': [torch.arange(_weight_of(self.tables[k]).shape[0], dtype=torch.int64,
+                                           device=self.device) for k in self.local_idx]}
+    flat = self._dense['flat']
+    flat.zero_()
+    views, o = [], 0
+    for k in self.local_idx:
+      w = _weight_of(self.tables[k])
+      views.append(flat[o:o + w.numel()].view(w.shape))
+      o += w.numel()
+    # (1) densify
+    feats = (_lib.hbUpdateFeature * m)()
+    for j, k in enumerate(self.local_idx):
+      w = _weight_of(self.tables[k])
+      feats[j] = _lib.hbUpdateFeature(
+          views[j].data_ptr(), None, None, w.shape[0], ids[k].data_ptr(),
+          offsets[k].data_ptr() if offsets[k] is not None else None, B, ids[k].numel(),
+          grad[:, self.col_offsets[k]:].data_ptr(), grad.stride(0), w.shape[1],
+          _lib.COMBINER[self.combiners[k]], 1)
+    ws = self._workspace(feats)
+    neg = _lib.hbOptimizer(_lib.OPT['sgd'], -1.0, 0.0, 0.0, 0.0, 0, 1)
+    if self._sort_done is not None:
+      torch.cuda.current_stream().wait_event(self._sort_done)
+      self._sort_done = None
+      _lib.check(L.hbGroupSparseApply(
+          m, feats, _lib.C.byref(neg), _lib.C.c_void_p(ws.data_ptr()), _lib.C.c_size_t(ws.numel()),
+          _lib.C.c_void_p(st.data_ptr()), _util.stream_ptr()), 'GroupLookup densify')
+    else:
+      _lib.check(L.hbGroupLookupBackwardUpdate(
+          m, feats, _lib.C.byref(neg), _lib.C.c_void_p(ws.data_ptr()), _lib.C.c_size_t(ws.numel()),
+          _lib.C.c_void_p(st.data_ptr()), _util.stream_ptr()), 'GroupLookup densify')
+    # (2) all-reduce, mean
+    self.collective.allreduce(flat, scale=1.0 / W, out=flat)
+    # (3) dense apply
+    feats2 = (_lib.hbUpdateFeature * m)()
+    for j, k in enumerate(self.local_idx):
+      w = _weight_of(self.tables[k])
+      slots = self._slots(k, optimizer)
+      rows = self._dense['rows'][j]
+      feats2[j] = _lib.hbUpdateFeature(
+          w.data_ptr(), slots[0].data_ptr() if len(slots) > 0 else None,
+          slots[1].data_ptr() if len(slots) > 1 else None, w.shape[0], rows.data_ptr(), None,
+          w.shape[0], w.shape[0], views[j].data_ptr(), w.shape[1], w.shape[1], _lib.COMBINER['sum'], 1)
+    ws2 = self._workspace(feats2)
+    _lib.check(L.hbGroupLookupBackwardUpdate(
+        m, feats2, _lib.C.byref(desc), _lib.C.c_void_p(ws2.data_ptr()), _lib.C.c_size_t(ws2.numel()),
+        _lib.C.c_void_p(st.data_ptr()), _util.stream_ptr()), 'GroupLookup dense apply')
 
   def _slots(self, k, optimizer):
     t = self.tables[k]

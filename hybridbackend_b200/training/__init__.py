@@ -11,16 +11,23 @@ class SparseOptimizer:
   kind = 'sgd'
   num_slots = 0
 
-  def __init__(self, learning_rate):
+  def __init__(self, learning_rate, fast_math=False):
     self.learning_rate = float(learning_rate)
     self.step = 0
+    # fast_math: approximate sqrt/divide of the GPU (<= 2 ulp each, the arithmetic
+    # class of TF's GPU kernels) instead of the IEEE sequence of TF's CPU kernels
+    self.fast_math = bool(fast_math)
+
+  @property
+  def flags(self):
+    return _lib.OPT_FLAG_FAST_MATH if self.fast_math else 0
 
   def slot_init(self, slot):  # pylint: disable=unused-argument
     return 0.0
 
   def descriptor(self):
     return _lib.hbOptimizer(_lib.OPT[self.kind], self.learning_rate, 0.0, 0.0, 0.0,
-                            max(self.step, 1))
+                            self.flags, max(self.step, 1))
 
 
 class SGD(SparseOptimizer):
@@ -33,8 +40,8 @@ class Adagrad(SparseOptimizer):
   kind = 'adagrad'
   num_slots = 1
 
-  def __init__(self, learning_rate, initial_accumulator_value=0.1):
-    super().__init__(learning_rate)
+  def __init__(self, learning_rate, initial_accumulator_value=0.1, fast_math=False):
+    super().__init__(learning_rate, fast_math)
     self.initial_accumulator_value = float(initial_accumulator_value)
 
   def slot_init(self, slot):
@@ -48,10 +55,10 @@ class LazyAdam(SparseOptimizer):
   kind = 'lazy_adam'
   num_slots = 2
 
-  def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8):
-    super().__init__(learning_rate)
+  def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8, fast_math=False):
+    super().__init__(learning_rate, fast_math)
     self.beta1, self.beta2, self.epsilon = float(beta1), float(beta2), float(epsilon)
 
   def descriptor(self):
     return _lib.hbOptimizer(_lib.OPT[self.kind], self.learning_rate, self.beta1,
-                            self.beta2, self.epsilon, max(self.step, 1))
+                            self.beta2, self.epsilon, self.flags, max(self.step, 1))

@@ -51,7 +51,10 @@ enum { HB_K_PART_HIST = 1, HB_K_PART_PASS = 2, HB_K_RESERVED3 = 3,
        HB_K_BARRIER = 13, HB_K_A2A_SIZES = 14, HB_K_A2A_TABLES = 15,
        HB_K_A2A_PUSH = 16, HB_K_A2A_COPYOUT = 17, HB_K_SH_EXCHANGE = 18,
        HB_K_SH_PUSH_IDS = 19, HB_K_SH_OWNER_GATHER = 20, HB_K_SH_STITCH = 21,
-       HB_K_SH_PUSH_GRADS = 22, HB_K_SH_PAD = 23, HB_K_COUNT = 24 };
+       HB_K_SH_PUSH_GRADS = 22, HB_K_SH_PAD = 23, HB_K_AR_PUSH = 24,
+       HB_K_AR_REDUCE = 25, HB_K_RUNS = 26, HB_K_UPDATE_LONG = 27,
+       HB_K_SH_PUBLISH = 28, HB_K_SH_UNIQUE = 29, HB_K_H2D_STAGE = 30,
+       HB_K_COUNT = 32 };
 
 const char* hbGetLastErrorString(void);
 /* number of kernels this library has launched in this process */
@@ -119,6 +122,8 @@ typedef struct hbLookupFeature {
   int32_t dim;
   int32_t combiner;       /* HB_SUM / HB_MEAN / HB_SQRTN */
   int64_t id_div;         /* >= 1 */
+  int64_t nnz;            /* number of ids; == nbags when offsets == NULL.  A bag
+                           * reaching beyond it raises HB_STATUS_BAD_OFFSETS. */
 } hbLookupFeature;
 
 int hbGroupLookupForward(int n, const hbLookupFeature* feats, int32_t* d_status,
@@ -151,10 +156,17 @@ typedef struct hbUpdateFeature {
   int64_t id_div;
 } hbUpdateFeature;
 
+/* hbOptimizer.flags: HB_OPT_FLAG_FAST_MATH computes the step with the GPU's
+ * approximate sqrt / divide (sqrt.approx, div.approx: <= 2 ulp each -- the class of
+ * arithmetic TF's GPU kernels use, which call rsqrt) instead of the IEEE
+ * sqrt-then-divide sequence of TF's CPU kernels; default 0 = bit-exact with the
+ * CPU semantics. */
+enum { HB_OPT_FLAG_FAST_MATH = 1 };
 typedef struct hbOptimizer {
   int32_t kind;           /* HB_OPT_* */
   float lr;
   float beta1, beta2, eps; /* LazyAdam */
+  int32_t flags;          /* HB_OPT_FLAG_* */
   int64_t step;           /* 1-based, LazyAdam bias correction */
 } hbOptimizer;
 
@@ -211,7 +223,19 @@ typedef struct hbComm hbComm;
 int hbCommCreate(int rank, int world_size, int local_size, size_t window_bytes,
                  hbComm** comm, unsigned char token_out[HB_COMM_TOKEN_BYTES]);
 int hbCommConnect(hbComm* comm, const unsigned char* all_tokens /* world*128 */);
+/* In-process group: world_size communicators on the CURRENT device whose peer
+ * windows are each other's allocations (no IPC, no second GPU).  One host thread
+ * per rank then drives comms[r] through the very same entry points and kernels
+ * as one process per GPU would; every collective entry point of a group member
+ * blocks until all ranks of the group have issued the same call (see
+ * csrc/comm.cuh comm_submit), so ranks MUST run on separate threads.  Built so
+ * that a single-GPU CI box exercises the multi-rank kernels; also usable to run
+ * W logical shards on one GPU. */
+int hbCommCreateLocalGroup(int world_size, size_t window_bytes, hbComm** comms /* [world] */);
 int hbCommDestroy(hbComm* comm);
+/* Sticky device status word (HB_STATUS_* bits) for the kernels of entry points
+ * that take none (barrier, size exchange); NULL detaches it. */
+int hbCommSetStatusWord(hbComm* comm, int32_t* d_status);
 int hbCommRank(const hbComm* comm);
 int hbCommWorldSize(const hbComm* comm);
 /* device pointer of the local window (tests / zero-copy producers) */
@@ -243,6 +267,18 @@ int hbAlltoallvNSizes(hbComm* comm, int n, const int32_t* const* d_send_sizes,
 int hbAlltoallvN(hbComm* comm, int n, const void* const* d_inputs,
                  const int64_t* common_sizes, const int32_t* elem_bytes,
                  void* const* d_outputs, int32_t* d_status, hbStream stream);
+
+/* ---------------------------------------------------------------------------
+ * Small dense all-reduce (fp32 sum, then * scale) over the peer windows.
+ * Replaces Collective.allreduce for the DENSE gradients of replicated "small"
+ *   embedding tables (training/gradient.py:132-141 densify, :157-160 allreduce,
+ *   :77-97 + :216 the 1/W mean -> pass scale = 1.0f / world).  Every rank adds the
+ *   W contributions in rank order, so all replicas get bit-identical results.
+ *   Moves W x count floats per rank: for small tables, not for model gradients.
+ *   Needs (window_bytes - plan bytes)/2 >= world * count * 4.  d_in == d_out ok.
+ * ------------------------------------------------------------------------- */
+int hbAllreduceSumF32(hbComm* comm, const float* d_in, float* d_out, int64_t count,
+                      float scale, int32_t* d_status, hbStream stream);
 
 /* ---------------------------------------------------------------------------
  * K1+K2+K3+K4 fused: sharded GroupLookup (additive op; its oracle is the

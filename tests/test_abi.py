@@ -51,7 +51,7 @@ def test_partition_workspace_query_and_validation(hb):
 
 def test_lookup_validation(hb):
   L = hb._lib.lib()
-  f = (hb._lib.hbLookupFeature * 1)(hb._lib.hbLookupFeature(None, 10, None, None, 0, None, 6, 6, 1, 1))
+  f = (hb._lib.hbLookupFeature * 1)(hb._lib.hbLookupFeature(None, 10, None, None, 0, None, 6, 6, 1, 1, 0))
   assert L.hbGroupLookupForward(1, f, None, None) == 1
   assert b'multiple of 4' in L.hbGetLastErrorString()
   assert L.hbGroupLookupForward(0, f, None, None) == 1

@@ -109,3 +109,14 @@ def test_criteo_shape_full_size_properties(hb):
   # linearity: lookup(2*T) == 2*lookup(T) exactly in fp32
   out2 = hb.embedding.embedding_lookup_sparse(tables[0] * 2, ids[0])
   assert torch.equal(out2, 2 * out[:, :D])
+
+
+def test_offsets_beyond_the_id_buffer_are_flagged(hb):
+  """A bag reaching past nnz raises BAD_OFFSETS instead of reading past the ids
+  (ADVICE round 1)."""
+  t = torch.randn(50, 8, device='cuda')
+  ids = torch.arange(10, device='cuda')
+  off = torch.tensor([0, 4, 25], device='cuda')  # second bag claims ids[4:25], nnz is 10
+  hb.embedding.embedding_lookup_sparse(t, ids, off, combiner='sum')
+  with pytest.raises(ValueError):
+    hb._util.check_status(t.device)
