@@ -33,8 +33,8 @@ namespace hb {
 
 constexpr int kBucketThreads = 256;
 constexpr int kBucketWarps = kBucketThreads / 32;
-constexpr int kBucketItems = 8;
-constexpr int kBucketTile = kBucketThreads * kBucketItems;  // 2048
+constexpr int kBucketItems = 16;
+constexpr int kBucketTile = kBucketThreads * kBucketItems;  // 4096
 constexpr int kMaxSegs = 128;
 constexpr int kMaxBins = 512;
 constexpr int kMaxPasses = 4;
@@ -223,11 +223,20 @@ __device__ __forceinline__ int32_t block_excl_scan(int32_t x, int32_t* s_warp /*
 
 // ---- hist -------------------------------------------------------------------
 // Histograms of every digit position of every segment in one read of the input.
+// digit of an already converted key (radix traits) / bin of a raw id (modulo traits)
+template <typename Tr>
+__device__ __forceinline__ int bin_of(typename Tr::In raw, typename Tr::Out key, const BucketParams& P,
+                                      const BucketSeg& sg, int shift) {
+  if constexpr (Tr::kRadix) return (int)((key >> shift) & (uint32_t)(P.nbins - 1));
+  else return Tr::bin(raw, P, sg, shift);
+}
+
 template <typename Tr>
 __global__ void __launch_bounds__(kBucketThreads)
 bucket_hist_kernel(const __grid_constant__ BucketParams P) {
   extern __shared__ uint32_t s_hist[];  // [npass][nbins]
   using In = typename Tr::In;
+  using Out = typename Tr::Out;
   const int nb = P.nbins;
   for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
     const int s = find_seg(P, tile);
@@ -238,20 +247,21 @@ bucket_hist_kernel(const __grid_constant__ BucketParams P) {
     const int base = t * kBucketTile;
     if (base >= n) continue;  // uniform per CTA
     for (int b = threadIdx.x; b < np * nb; b += kBucketThreads) s_hist[b] = 0;
-    __syncthreads();
     const In* in = reinterpret_cast<const In*>(sg.in_keys);
+    In v[kBucketItems];
+#pragma unroll
+    for (int j = 0; j < kBucketItems; ++j) {  // all loads in flight together
+      const int i = base + j * kBucketThreads + threadIdx.x;
+      v[j] = (i < n) ? in[i] : In(0);
+    }
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < kBucketItems; ++j) {
       const int i = base + j * kBucketThreads + threadIdx.x;
-      const bool valid = i < n;
-      In v = In(0);
-      if (valid) v = in[i];
-      for (int p = 0; p < np; ++p) {
-        int b = -1;
-        if (valid) b = Tr::bin(v, P, sg, p * P.digit_bits);
-        // warp-aggregate: one shared atomic per distinct bin per warp
-        const unsigned peers = __match_any_sync(0xffffffffu, b);
-        if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&s_hist[p * nb + b], __popc(peers));
+      if (i < n) {
+        const Out key = Tr::conv(v[j], P, sg);  // converted once, every digit taken from it
+        for (int p = 0; p < np; ++p)
+          atomicAdd(&s_hist[p * nb + bin_of<Tr>(v[j], key, P, sg, p * P.digit_bits)], 1u);
       }
     }
     __syncthreads();
@@ -272,7 +282,7 @@ bucket_hist_kernel(const __grid_constant__ BucketParams P) {
 
 // ---- pass -------------------------------------------------------------------
 template <typename Tr>
-__global__ void __launch_bounds__(kBucketThreads, 4)
+__global__ void __launch_bounds__(kBucketThreads, 3)
 bucket_pass_kernel(const __grid_constant__ BucketParams P) {
   using In = typename Tr::In;
   using Out = typename Tr::Out;
@@ -307,31 +317,56 @@ bucket_pass_kernel(const __grid_constant__ BucketParams P) {
   for (int b = threadIdx.x; b < kBucketWarps * nb; b += kBucketThreads) s_wcnt[b] = 0;
   __syncthreads();
 
-  // 1. per-warp stable ranks over the warp's contiguous slice
+  // 1. per-warp stable ranks over the warp's contiguous slice.  Everything the tile
+  //    needs from global memory is requested up front (keys, carried values, the
+  //    histogram row): one exposed round trip instead of three.
   const int wbase = t * kBucketTile + warp * (kBucketItems * 32);
-  In key[kBucketItems];
-  int32_t rank[kBucketItems];
-  int bin[kBucketItems];
+  Out key[kBucketItems];
+  int32_t val[kBucketItems];
+  uint32_t rb[kBucketItems];  // stable rank inside the warp slice (low 16 bits) | bin (high 16; kNoBin: none)
+  constexpr uint32_t kNoBin = 0xFFFFu;
+  const bool carry_vals = sg.out_vals != nullptr && sg.in_vals != nullptr;
+  {
+    In raw[kBucketItems];
 #pragma unroll
-  for (int j = 0; j < kBucketItems; ++j) {
-    const int i = wbase + j * 32 + lane;
-    key[j] = (i < n) ? in[i] : In(0);
+    for (int j = 0; j < kBucketItems; ++j) {
+      const int i = wbase + j * 32 + lane;
+      raw[j] = (i < n) ? in[i] : In(0);
+    }
+#pragma unroll
+    for (int j = 0; j < kBucketItems; ++j) {
+      const int i = wbase + j * 32 + lane;
+      val[j] = (carry_vals && i < n) ? sg.in_vals[i] : i;
+    }
+#pragma unroll
+    for (int j = 0; j < kBucketItems; ++j) {
+      const int i = wbase + j * 32 + lane;
+      key[j] = Tr::conv(raw[j], P, sg);
+      rb[j] = ((i < n) ? (uint32_t)bin_of<Tr>(raw[j], key[j], P, sg, sg.shift) : kNoBin) << 16;
+    }
+  }
+  const uint32_t* gh = P.hist + ((size_t)sg.hist_slot * P.npass + P.pass) * nb;
+  int32_t hpre[kBinsPerThread];
+#pragma unroll
+  for (int k = 0; k < kBinsPerThread; ++k) {
+    const int b = threadIdx.x * kBinsPerThread + k;
+    hpre[k] = (b < nb) ? (int32_t)gh[b] : 0;
   }
   int32_t* wc = s_wcnt + warp * nb;
 #pragma unroll
   for (int j = 0; j < kBucketItems; ++j) {
     const int i = wbase + j * 32 + lane;
     const bool valid = i < n;
-    bin[j] = valid ? Tr::bin(key[j], P, sg, sg.shift) : -1;
-    const unsigned peers = __match_any_sync(0xffffffffu, bin[j]);
+    const uint32_t b = rb[j] >> 16;
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
     const int leader = __ffs(peers) - 1;
     int32_t base = 0;
     if (valid && lane == (unsigned)leader) {
-      base = wc[bin[j]];
-      wc[bin[j]] = base + __popc(peers);
+      base = wc[b];
+      wc[b] = base + __popc(peers);
     }
     base = __shfl_sync(0xffffffffu, base, leader);
-    rank[j] = base + __popc(peers & lanemask_lt());
+    rb[j] |= (uint32_t)(base + __popc(peers & lanemask_lt()));
     __syncwarp();
   }
   __syncthreads();
@@ -357,15 +392,13 @@ bucket_pass_kernel(const __grid_constant__ BucketParams P) {
   }
 
   // 3. bin bases from the global histogram (exclusive scan over bins) ...
-  const uint32_t* gh = P.hist + ((size_t)sg.hist_slot * P.npass + P.pass) * nb;
   {
     // thread owns bins {2*tid, 2*tid+1} for the scan (contiguous), totals from hist
     int32_t h[kBinsPerThread];
     int32_t hsum = 0;
 #pragma unroll
     for (int k = 0; k < kBinsPerThread; ++k) {
-      const int b = threadIdx.x * kBinsPerThread + k;
-      h[k] = (b < nb) ? (int32_t)gh[b] : 0;
+      h[k] = hpre[k];
       hsum += h[k];
     }
     int32_t run = block_excl_scan(hsum, s_scan, nullptr);
@@ -392,20 +425,21 @@ bucket_pass_kernel(const __grid_constant__ BucketParams P) {
     int32_t pre[kBinsPerThread];
 #pragma unroll
     for (int k = 0; k < kBinsPerThread; ++k) pre[k] = 0;
-    for (int tp = 0; tp < t; tp += 8) {
-      uint32_t v[kBinsPerThread][8];
+    constexpr int kLook = 4;
+    for (int tp = 0; tp < t; tp += kLook) {
+      uint32_t v[kBinsPerThread][kLook];
 #pragma unroll
       for (int k = 0; k < kBinsPerThread; ++k) {
         const int b = k * kBucketThreads + threadIdx.x;
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < kLook; ++u)
           v[k][u] = (b < nb && tp + u < t) ? ld_volatile_u32(st + (size_t)(tp + u) * nb + b) : kReady;
       }
 #pragma unroll
       for (int k = 0; k < kBinsPerThread; ++k) {
         const int b = k * kBucketThreads + threadIdx.x;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kLook; ++u) {
           while (!(v[k][u] & kReady)) v[k][u] = ld_volatile_u32(st + (size_t)(tp + u) * nb + b);
           pre[k] += (int32_t)(v[k][u] & ~kReady);
         }
@@ -451,13 +485,12 @@ bucket_pass_kernel(const __grid_constant__ BucketParams P) {
   for (int j = 0; j < kBucketItems; ++j) {
     const int i = wbase + j * 32 + lane;
     if (i < n) {
-      const int b = bin[j];
-      const int32_t in_bin = s_wcnt[warp * nb + b] + rank[j];
+      const int b = (int)(rb[j] >> 16);
+      const int32_t in_bin = s_wcnt[warp * nb + b] + (int32_t)(rb[j] & 0xFFFFu);
       const int32_t lpos = s_lstart[b] + in_bin;
-      s_keys[lpos] = Tr::conv(key[j], P, sg);
+      s_keys[lpos] = key[j];
       s_bin[lpos] = (uint16_t)b;
-      if (sg.out_vals != nullptr)
-        s_vals[lpos] = (sg.in_vals != nullptr) ? sg.in_vals[i] : i;
+      if (sg.out_vals != nullptr) s_vals[lpos] = val[j];
       if (sg.out_inv != nullptr) sg.out_inv[i] = s_gbase[b] + in_bin;
     }
   }

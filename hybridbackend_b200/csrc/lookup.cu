@@ -11,7 +11,12 @@
 // (one-id-per-bag fast path) or 4 ids of one bag in flight.
 //
 // HBM traffic per pooled row (algorithmic): L*(8 + 4*dim) read + 4*dim written.
+#include <stdlib.h>
+
+#include <vector>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace hb {
 
@@ -234,6 +239,162 @@ lookup_fwd_kernel(const __grid_constant__ LookupParams P) {
   if (bad_off) raise_status(P.status, HB_STATUS_BAD_OFFSETS);
 }
 
+
+// ---- one id per bag: pure row gather through the copy engine --------------------------
+// out[b, :] = table[row(ids[b]), :].  No register ever holds row data: a lane starts
+// a 1-D bulk copy (cp.async.bulk, SASS UBLKCP) of each of its rows into the warp's
+// shared-memory stage, the copies complete on the warp's mbarrier, and the staged
+// rows leave again as bulk stores into the concatenated output.  Three stages per
+// warp rotate, so the loads of the next block of rows are in flight while the
+// current one drains: kLtWarps x kLtStages x kLtStageBytes = 192 KB of rows in
+// flight per SM, against ~16 KB with 128-bit register loads.
+constexpr int kLtWarps = 8;
+constexpr int kLtStages = 3;
+constexpr int kLtStageBytes = 8192;
+constexpr int kLtMaxRows = 64;   // rows per stage at most (two per lane)
+
+struct LtFeat {
+  const float* table;
+  const int64_t* ids;
+  float* out;
+  int64_t rows;
+  int64_t out_stride;
+  int64_t id_div;
+  int32_t nbags;
+  int32_t dim;
+  int32_t div_shift;
+  int32_t unit_begin;   // first work unit of this feature
+  int32_t rows_per_unit;
+};
+
+struct LtParams {
+  LtFeat f[kMaxLookupFeats];
+  int32_t* status;
+  int32_t nfeats;
+  int32_t total_units;
+};
+
+__device__ __forceinline__ int lt_find(const LtParams& P, int unit) {
+  int lo = 0, hi = P.nfeats - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (P.f[mid].unit_begin <= unit) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// start the copies of one unit into stage `buf`; returns through the barrier
+__device__ __forceinline__ void lt_issue(const LtParams& P, int unit, float* buf, uint64_t* bar,
+                                         unsigned lane, bool& oob) {
+  const int fi = lt_find(P, unit);
+  const LtFeat& F = P.f[fi];
+  const uint32_t row_bytes = (uint32_t)F.dim * 4u;
+  const int b0 = (unit - F.unit_begin) * F.rows_per_unit;
+  int64_t idv[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int slot = r * 32 + (int)lane;
+    const int b = b0 + slot;
+    idv[r] = (slot < F.rows_per_unit && b < F.nbags) ? ld_nc_i64(F.ids + b) : (int64_t)-1;
+  }
+  uint32_t bytes = 0;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int slot = r * 32 + (int)lane;
+    const int b = b0 + slot;
+    const bool in_unit = slot < F.rows_per_unit && b < F.nbags;
+    int64_t row = -1;
+    if (in_unit && idv[r] >= 0)
+      row = F.div_shift >= 0 ? (int64_t)((uint64_t)idv[r] >> F.div_shift) : idv[r] / F.id_div;
+    const bool ok = in_unit && (uint64_t)row < (uint64_t)F.rows;
+    if (in_unit && !ok) {   // out-of-range id: the output row is zeros
+      oob = true;
+      float4* z = reinterpret_cast<float4*>(buf + (size_t)slot * F.dim);
+      for (int c = 0; c < F.dim / 4; ++c) z[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (ok) bulk_g2s(buf + (size_t)slot * F.dim, F.table + row * F.dim, row_bytes, bar);
+    bytes += __popc(__ballot_sync(0xffffffffu, ok)) * row_bytes;
+  }
+  if (lane == 0) mbar_arrive_expect_tx(bar, bytes);
+}
+
+__device__ __forceinline__ void lt_store(const LtParams& P, int unit, const float* buf, unsigned lane) {
+  const int fi = lt_find(P, unit);
+  const LtFeat& F = P.f[fi];
+  const uint32_t row_bytes = (uint32_t)F.dim * 4u;
+  const int b0 = (unit - F.unit_begin) * F.rows_per_unit;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int slot = r * 32 + (int)lane;
+    const int b = b0 + slot;
+    if (slot < F.rows_per_unit && b < F.nbags)
+      bulk_s2g(F.out + (int64_t)b * F.out_stride, buf + (size_t)slot * F.dim, row_bytes);
+  }
+  bulk_commit();
+}
+
+__global__ void __launch_bounds__(kLtWarps * 32, 1)
+lookup_rows_tma_kernel(const __grid_constant__ LtParams P) {
+  extern __shared__ __align__(128) unsigned char s_lt[];
+  __shared__ uint64_t s_bar[kLtWarps][kLtStages];
+  const unsigned lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int s = 0; s < kLtStages; ++s) mbar_init(&s_bar[warp][s], 1);
+  mbar_init_fence();
+  __syncthreads();
+  float* stage0 = reinterpret_cast<float*>(s_lt + (size_t)warp * kLtStages * kLtStageBytes);
+  const int stride = gridDim.x * kLtWarps;
+  int unit = blockIdx.x * kLtWarps + warp;
+  uint32_t parity = 0;   // bit s: parity of the next completion of stage s
+  bool oob = false;
+  // prologue: two units in flight
+  int st = 0;
+  if (unit < P.total_units) lt_issue(P, unit, stage0, &s_bar[warp][0], lane, oob);
+  if (unit + stride < P.total_units)
+    lt_issue(P, unit + stride, stage0 + kLtStageBytes / 4, &s_bar[warp][1], lane, oob);
+  while (unit < P.total_units) {
+    mbar_wait(&s_bar[warp][st], (parity >> st) & 1u);
+    parity ^= 1u << st;
+    fence_proxy_async();   // zero rows written with ordinary stores -> visible to the bulk stores
+    lt_store(P, unit, stage0 + (size_t)st * (kLtStageBytes / 4), lane);
+    // refill the stage drained in the PREVIOUS iteration: its bulk stores must have
+    // finished reading shared memory (all store groups but the one just committed)
+    const int ahead = unit + 2 * stride;
+    const int st2 = (st + 2) % kLtStages;
+    if (ahead < P.total_units) {
+      bulk_wait_read<1>();
+      __syncwarp();
+      lt_issue(P, ahead, stage0 + (size_t)st2 * (kLtStageBytes / 4), &s_bar[warp][st2], lane, oob);
+    }
+    unit += stride;
+    st = (st + 1) % kLtStages;
+  }
+  bulk_wait<0>();          // global writes complete before the kernel ends
+  if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
+}
+
+static bool use_tma_gather() {
+  static const bool on = [] {
+    const char* e = getenv("HB_NO_TMA");
+    return !(e != nullptr && e[0] == '1');
+  }();
+  return on;
+}
+
+static int launch_rows_tma(const LtParams& P, cudaStream_t stream, int kid) {
+  if (P.total_units == 0) return HB_OK;
+  const size_t smem = (size_t)kLtWarps * kLtStages * kLtStageBytes;
+  HB_CUDA_OK(cudaFuncSetAttribute(lookup_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = device_sm_count();
+  const int need = (P.total_units + kLtWarps - 1) / kLtWarps;
+  if (grid > need) grid = need;
+  KernelScope ks(kid, stream);
+  lookup_rows_tma_kernel<<<grid, kLtWarps * 32, smem, stream>>>(P);
+  HB_CUDA_OK(cudaGetLastError());
+  return HB_OK;
+}
+
 static int ilog2_ceil(int x) {
   int l = 0;
   while ((1 << l) < x) ++l;
@@ -300,6 +461,42 @@ int lookup_forward_run(int n, const hbLookupFeature* feats, const int32_t* const
     if (rc != HB_OK) return rc;
   }
   bool waited = false;
+  // one id per bag, local table, no peer-written data: the copy-engine gather
+  std::vector<char> done(n, 0);
+  if (use_tma_gather() && wait == nullptr && !coherent) {
+    LtParams T;
+    T.status = d_status;
+    T.nfeats = 0;
+    T.total_units = 0;
+    auto flush_t = [&]() -> int {
+      const int rc = T.nfeats > 0 ? launch_rows_tma(T, stream, kernel_id) : HB_OK;
+      T.nfeats = 0;
+      T.total_units = 0;
+      return rc;
+    };
+    for (int k = 0; k < n; ++k) {
+      const hbLookupFeature& f = feats[k];
+      if (f.offsets != nullptr || (idx32 != nullptr && idx32[k] != nullptr) || f.nbags == 0) continue;
+      if (f.dim * 4 > kLtStageBytes / 2 || ((uintptr_t)f.out & 15) || (f.out_stride & 3)) continue;
+      LtFeat& F = T.f[T.nfeats++];
+      F.table = f.table; F.ids = f.ids; F.out = f.out;
+      F.rows = f.rows; F.out_stride = f.out_stride; F.id_div = f.id_div;
+      F.nbags = (int32_t)f.nbags; F.dim = f.dim;
+      F.div_shift = ((f.id_div & (f.id_div - 1)) == 0 && f.id_div <= (1 << 30)) ? ilog2_ceil((int)f.id_div) : -1;
+      int rpu = kLtStageBytes / (f.dim * 4);
+      if (rpu > kLtMaxRows) rpu = kLtMaxRows;
+      F.rows_per_unit = rpu;
+      F.unit_begin = T.total_units;
+      T.total_units += (int)((f.nbags + rpu - 1) / rpu);
+      done[k] = 1;
+      if (T.nfeats == kMaxLookupFeats) {
+        const int rc = flush_t();
+        if (rc != HB_OK) return rc;
+      }
+    }
+    const int rc = flush_t();
+    if (rc != HB_OK) return rc;
+  }
   // one launch per distinct V (1 for every dim <= 128), chunks of kMaxLookupFeats
   for (int V = 1; V <= 8; V <<= 1) {
     LookupParams P;
@@ -327,7 +524,7 @@ int lookup_forward_run(int n, const hbLookupFeature* feats, const int32_t* const
       const hbLookupFeature& f = feats[k];
       int log2g, v;
       lookup_shape(f.dim, &log2g, &v);
-      if (v != V || f.nbags == 0) continue;
+      if (v != V || f.nbags == 0 || done[k]) continue;
       LookupFeat& F = P.f[P.nfeats];
       F.table = f.table; F.ids = f.ids; F.offsets = f.offsets; F.out = f.out;
       F.idx32 = idx32 ? idx32[k] : nullptr;

@@ -27,6 +27,7 @@
 #include <math.h>
 
 #include "bucket.cuh"
+#include "tma.cuh"
 #include "update.cuh"
 
 namespace hb {
@@ -34,7 +35,6 @@ namespace hb {
 constexpr int kUpdThreads = 256;
 constexpr int kMaxUpdFeats = 96;
 constexpr int kShortMax = 16;   // runs up to this many entries are summed by one group
-constexpr int kPiece = 256;     // entries per piece of a long run (one warp)
 constexpr int kNU = 2;          // unique rows in flight per group (short kernel)
 
 enum { kModeApply = 0, kModeEmit = 1 };
@@ -48,6 +48,7 @@ struct UpdFeat {
   const uint32_t* ukey;     // [U] unique keys
   const int32_t* ustart;    // [U+1]
   const int32_t* counts;    // [0] = U
+  const int32_t* uval;      // [U] value of the first entry of each run
   const int32_t* vals;      // bag index of each sorted entry (or its position, see pos2bag)
   const int32_t* pos2bag;   // != nullptr: vals hold input positions, bag = pos2bag[position]
   const int32_t* emit_send_off;
@@ -60,6 +61,7 @@ struct UpdFeat {
   int32_t combiner;
   int32_t log2g;
   int32_t max_chunks;       // static bound of the number of chunks of this feature
+  int32_t piece;            // entries per piece of a long run (kStageBytes of rows)
 };
 
 struct LongItem { int32_t feat, u, piece, pbase; };
@@ -240,14 +242,15 @@ __device__ __forceinline__ int seg_find(const int* s_begin, int nsegs, int unit)
 }
 
 // ---- 3. runs ----------------------------------------------------------------------------
-constexpr int kRunItems = 8;
-constexpr int kRunTile = kUpdThreads * kRunItems;  // 2048
+constexpr int kRunItems = 16;
+constexpr int kRunTile = kUpdThreads * kRunItems;  // 4096
 
 struct RunFeat {
   const uint32_t* keys;   // sorted
   const int32_t* vals;
   uint32_t* ukey;
   int32_t* ustart;
+  int32_t* uval;          // value (bag / position) of the first entry of every run
   int32_t* counts;        // [0] = U, [1] = valid entries
   int32_t* inv;           // may be nullptr
   int32_t* owner_start1;  // may be nullptr
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(kUpdThreads) runs_kernel(const __grid_constant
   __shared__ int s_begin[kMaxUpdFeats + 1];
   __shared__ int32_t s_scan[kBucketWarps];
   __shared__ int s_tile;
+  __shared__ int32_t s_pre;
   const int tid = threadIdx.x;
   int units = 0;
   if (tid < P.nfeats) {
@@ -294,46 +298,57 @@ __global__ void __launch_bounds__(kUpdThreads) runs_kernel(const __grid_constant
     const int t = tile - s_begin[fi];
     const int n = run_len(F);
     const int i0 = t * kRunTile + tid * kRunItems;
-    // k[0] = key of the entry before mine, k[1..8] mine, k[9] the one after
+    // k[0] = key of the entry before mine, k[1..16] mine, k[17] the one after
     uint32_t k[kRunItems + 2];
+    if (i0 + kRunItems <= n) {  // 64-byte aligned run of 16 keys: four 128-bit loads
+      const uint4* p = reinterpret_cast<const uint4*>(F.keys + i0);
 #pragma unroll
-    for (int j = 0; j < kRunItems + 2; ++j) {
-      const int i = i0 - 1 + j;
-      k[j] = (i >= 0 && i < n) ? F.keys[i] : 0xFFFFFFFFu;
+      for (int q = 0; q < kRunItems / 4; ++q) {
+        const uint4 v = p[q];
+        k[1 + 4 * q] = v.x; k[2 + 4 * q] = v.y; k[3 + 4 * q] = v.z; k[4 + 4 * q] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kRunItems; ++j) k[j + 1] = (i0 + j < n) ? F.keys[i0 + j] : 0xFFFFFFFFu;
     }
-    bool head[kRunItems];
-    int cnt = 0;
+    k[0] = (i0 > 0 && i0 - 1 < n) ? F.keys[i0 - 1] : 0xFFFFFFFFu;
+    k[kRunItems + 1] = (i0 + kRunItems < n) ? F.keys[i0 + kRunItems] : 0xFFFFFFFFu;
+    uint32_t heads = 0;
 #pragma unroll
     for (int j = 0; j < kRunItems; ++j) {
       const int i = i0 + j;
       const bool valid = i < n && k[j + 1] < 0xFFFFFFFEu;
       if (i < n && k[j + 1] == 0xFFFFFFFEu) oob = true;
-      head[j] = valid && (i == 0 || k[j + 1] != k[j]);
-      cnt += head[j] ? 1 : 0;
+      if (valid && (i == 0 || k[j + 1] != k[j])) heads |= 1u << j;
     }
     int32_t tile_total;
-    const int32_t excl = block_excl_scan(cnt, s_scan, &tile_total);
+    const int32_t excl = block_excl_scan(__popc(heads), s_scan, &tile_total);
     if (tid == 0)
       *reinterpret_cast<volatile uint32_t*>(&P.status[tile]) = (uint32_t)tile_total | kReady;
-    // uniques in the preceding tiles of this feature
-    int32_t pre = 0;
-    for (int tp = tid; tp < t; tp += kUpdThreads) {
-      const uint32_t* w = P.status + s_begin[fi] + tp;
-      uint32_t v = ld_volatile_u32(w);
-      while (!(v & kReady)) v = ld_volatile_u32(w);
-      pre += (int32_t)(v & ~kReady);
+    // uniques in the preceding tiles of this feature: summed by the first warp
+    if (tid < 32) {
+      int32_t pre = 0;
+      for (int tp = tid; tp < t; tp += 32) {
+        const uint32_t* w = P.status + s_begin[fi] + tp;
+        uint32_t v = ld_volatile_u32(w);
+        while (!(v & kReady)) v = ld_volatile_u32(w);
+        pre += (int32_t)(v & ~kReady);
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, off);
+      if (tid == 0) s_pre = pre;
     }
-    int32_t pre_total;
-    block_excl_scan(pre, s_scan, &pre_total);
-    int u = pre_total + excl;  // index the next head of this thread gets
+    __syncthreads();
+    int u = s_pre + excl;  // index the next head of this thread gets
 #pragma unroll
     for (int j = 0; j < kRunItems; ++j) {
       const int i = i0 + j;
       if (i >= n) break;
       const bool valid = k[j + 1] < 0xFFFFFFFEu;
-      if (head[j]) {
+      if ((heads >> j) & 1u) {
         F.ukey[u] = k[j + 1];
         F.ustart[u] = i;
+        F.uval[u] = F.vals[i];
         if (F.owner_start1 != nullptr) {
           const uint32_t own = k[j + 1] >> F.lbits;
           if (i == 0 || (k[j] >> F.lbits) != own) F.owner_start1[own] = u + 1;
@@ -357,8 +372,8 @@ __global__ void __launch_bounds__(kUpdThreads) runs_kernel(const __grid_constant
 }
 
 // ---- 4. short runs ----------------------------------------------------------------------
-__device__ __forceinline__ void queue_long(const UpdParams& P, int fi, int u, int len) {
-  const int np = (len + kPiece - 1) / kPiece;
+__device__ __forceinline__ void queue_long(const UpdParams& P, const UpdFeat& F, int fi, int u, int len) {
+  const int np = (len + F.piece - 1) / F.piece;
   const int base = atomicAdd(&P.long_count[0], np);
   const int pb = np > 1 ? atomicAdd(&P.long_count[1], np) : -1;
   if (base + np > P.item_cap || (np > 1 && pb + np > P.part_cap)) {  // cannot happen by the layout bounds
@@ -366,6 +381,32 @@ __device__ __forceinline__ void queue_long(const UpdParams& P, int fi, int u, in
     return;
   }
   for (int j = 0; j < np; ++j) P.items[base + j] = LongItem{fi, u, j, pb};
+}
+
+// run bounds, key and first value of the kNU unique rows a group owns in `chunk`
+struct ShortMeta {
+  int fi;
+  int us[kNU], s[kNU], len[kNU], v0[kNU];
+  uint32_t key[kNU];
+};
+
+__device__ __forceinline__ void short_meta(const UpdParams& P, const int* s_begin, int chunk, ShortMeta& M) {
+  M.fi = seg_find(s_begin, P.nfeats, chunk);
+  const UpdFeat& F = P.f[M.fi];
+  const int groups = kUpdThreads >> F.log2g;
+  const int g = threadIdx.x >> F.log2g;
+  const int U = F.counts[0];
+  const int u0 = (chunk - s_begin[M.fi]) * groups * kNU;
+#pragma unroll
+  for (int q = 0; q < kNU; ++q) {  // consecutive groups <-> consecutive uniques (coalesced)
+    M.us[q] = u0 + q * groups + g;
+    const bool ok = M.us[q] < U;
+    const int uu = ok ? M.us[q] : 0;
+    M.s[q] = F.ustart[uu];
+    M.len[q] = ok ? F.ustart[uu + 1] - M.s[q] : 0;
+    M.key[q] = F.ukey[uu];
+    M.v0[q] = F.uval[uu];
+  }
 }
 
 template <int V, int OPT, int MODE, bool FAST>
@@ -382,16 +423,17 @@ update_short_kernel(const __grid_constant__ UpdParams P) {
   }
   const int total = seg_scan(P.nfeats, units, s_begin);
   bool oob = false;
-  for (int chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
-    const int fi = seg_find(s_begin, P.nfeats, chunk);
-    const UpdFeat& F = P.f[fi];
+  int chunk = blockIdx.x;
+  ShortMeta M, Mn;
+  if (chunk < total) short_meta(P, s_begin, chunk, M);
+  while (chunk < total) {
+    // the NEXT chunk's run bounds travel while this chunk's rows do
+    const int next = chunk + gridDim.x;
+    if (next < total) short_meta(P, s_begin, next, Mn);
+    const UpdFeat& F = P.f[M.fi];
     const int log2g = F.log2g;
-    const int groups = kUpdThreads >> log2g;
-    const int g = tid >> log2g;
     const int l = tid & ((1 << log2g) - 1);
     const int dim = F.dim;
-    const int U = F.counts[0];
-    const int u0 = (chunk - s_begin[fi]) * groups * kNU;
     const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
     int col[V];
     bool act[V];
@@ -400,88 +442,54 @@ update_short_kernel(const __grid_constant__ UpdParams P) {
       col[v] = ((v << log2g) + l) * 4;
       act[v] = col[v] < dim;
     }
-    // run bounds and keys of my kNU unique rows (consecutive groups <-> consecutive uniques)
-    int us[kNU], s[kNU], len[kNU];
-    uint32_t key[kNU];
     bool ok[kNU];
 #pragma unroll
     for (int q = 0; q < kNU; ++q) {
-      us[q] = u0 + q * groups + g;
-      ok[q] = us[q] < U;
-      const int uu = ok[q] ? us[q] : 0;
-      s[q] = F.ustart[uu];
-      len[q] = F.ustart[uu + 1] - s[q];
-      key[q] = F.ukey[uu];
-    }
-#pragma unroll
-    for (int q = 0; q < kNU; ++q) {
-      if (!ok[q]) len[q] = 0;
-      if (ok[q] && len[q] > kShortMax) {  // hot row: the long kernel sums it with whole warps
-        if (l == 0) queue_long(P, fi, us[q], len[q]);
+      ok[q] = M.len[q] > 0;
+      if (ok[q] && M.len[q] > kShortMax) {  // hot row: the long kernel sums it with whole warps
+        if (l == 0) queue_long(P, F, M.fi, M.us[q], M.len[q]);
         ok[q] = false;
-        len[q] = 0;
       }
-      if (MODE == kModeApply && ok[q] && (uint64_t)key[q] >= (uint64_t)F.rows) {
+      if (MODE == kModeApply && ok[q] && (uint64_t)M.key[q] >= (uint64_t)F.rows) {
         oob = true;
         ok[q] = false;
-        len[q] = 0;
       }
+      if (!ok[q]) M.len[q] = 0;
     }
-    // table / slot rows: their addresses only need the key, so they travel together
-    // with the bag indices; the gradient rows follow one round trip later
-    float4 w[kNU][V], s0[kNU][V], s1[kNU][V];
-    if constexpr (MODE == kModeApply) {
+    // one round trip: table row, slot rows and the gradient row of the run's first
+    // entry (its bag came with the run bounds)
+    float4 w[kNU][V], s0[kNU][V], s1[kNU][V], acc[kNU][V];
+    float sc0[kNU];
 #pragma unroll
-      for (int q = 0; q < kNU; ++q)
+    for (int q = 0; q < kNU; ++q) {
+      int bag0 = M.v0[q];
+      if (ok[q] && F.pos2bag != nullptr) bag0 = F.pos2bag[bag0];
+      sc0[q] = (scaled && ok[q]) ? bag_scale(F, bag0) : 1.0f;
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          w[q][v] = s0[q][v] = s1[q][v] = f4_zero();
-          if (ok[q] && act[v]) {
-            const int64_t o = (int64_t)key[q] * dim + col[v];
+      for (int v = 0; v < V; ++v) {
+        w[q][v] = s0[q][v] = s1[q][v] = acc[q][v] = f4_zero();
+        if (ok[q] && act[v]) {
+          acc[q][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.grad + (int64_t)bag0 * F.grad_stride + col[v]));
+          if constexpr (MODE == kModeApply) {
+            const int64_t o = (int64_t)M.key[q] * dim + col[v];
             w[q][v] = *reinterpret_cast<const float4*>(F.table + o);
             if constexpr (OPT != HB_OPT_SGD) s0[q][v] = *reinterpret_cast<const float4*>(F.slot0 + o);
             if constexpr (OPT == HB_OPT_LAZY_ADAM) s1[q][v] = *reinterpret_cast<const float4*>(F.slot1 + o);
           }
         }
-    }
-    // first two entries of every run, all in flight together (most runs end here)
-    int bag[kNU][2];
-#pragma unroll
-    for (int q = 0; q < kNU; ++q)
-#pragma unroll
-      for (int i = 0; i < 2; ++i) bag[q][i] = (i < len[q]) ? entry_bag(F, s[q] + i) : -1;
-    float4 gv[kNU][2][V];
-    float sc[kNU][2];
-#pragma unroll
-    for (int q = 0; q < kNU; ++q)
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        sc[q][i] = 1.0f;
-        if (scaled && bag[q][i] >= 0) sc[q][i] = bag_scale(F, bag[q][i]);
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          gv[q][i][v] = f4_zero();
-          if (bag[q][i] >= 0 && act[v])
-            gv[q][i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
-                F.grad + (int64_t)bag[q][i] * F.grad_stride + col[v]));
-        }
       }
-    float4 acc[kNU][V];
+    }
 #pragma unroll
     for (int q = 0; q < kNU; ++q) {
+      if (scaled) {
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        // the first term is taken as is (0 + g would turn -0 into +0), later terms are
-        // added in position order
-        acc[q][v] = scaled ? f4_div_rn(gv[q][0][v], sc[q][0]) : gv[q][0][v];
-        if (len[q] > 1)
-          acc[q][v] = f4_add_rn(acc[q][v], scaled ? f4_div_rn(gv[q][1][v], sc[q][1]) : gv[q][1][v]);
+        for (int v = 0; v < V; ++v) acc[q][v] = f4_div_rn(acc[q][v], sc0[q]);
       }
-      // entries 2 .. len-1 (rare), four at a time
-      for (int j0 = 2; j0 < len[q]; j0 += 4) {
+      // entries 1 .. len-1, four at a time, added in position order
+      for (int j0 = 1; j0 < M.len[q]; j0 += 4) {
         int b4[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) b4[i] = (j0 + i < len[q]) ? entry_bag(F, s[q] + j0 + i) : -1;
+        for (int i = 0; i < 4; ++i) b4[i] = (j0 + i < M.len[q]) ? entry_bag(F, M.s[q] + j0 + i) : -1;
         float4 x[4][V];
         float c4[4];
 #pragma unroll
@@ -512,32 +520,59 @@ update_short_kernel(const __grid_constant__ UpdParams P) {
 #pragma unroll
         for (int v = 0; v < V; ++v)
           if (act[v]) {
-            const int64_t o = (int64_t)key[q] * dim + col[v];
+            const int64_t o = (int64_t)M.key[q] * dim + col[v];
             opt_step4<OPT, FAST>(P, w[q][v], s0[q][v], s1[q][v], acc[q][v]);
             *reinterpret_cast<float4*>(F.table + o) = w[q][v];
             if constexpr (OPT != HB_OPT_SGD) *reinterpret_cast<float4*>(F.slot0 + o) = s0[q][v];
             if constexpr (OPT == HB_OPT_LAZY_ADAM) *reinterpret_cast<float4*>(F.slot1 + o) = s1[q][v];
           }
       } else {
-        sink_row<V, OPT, MODE, FAST>(P, F, key[q], us[q], acc[q], col, act, oob);
+        sink_row<V, OPT, MODE, FAST>(P, F, M.key[q], M.us[q], acc[q], col, act, oob);
       }
     }
+    M = Mn;
+    chunk = next;
   }
   if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
 }
 
 // ---- 5. long runs -----------------------------------------------------------------------
+// One warp per piece.  The piece's gradient rows are STAGED in shared memory by 1-D
+// bulk asynchronous copies (cp.async.bulk, the TMA engine): every lane issues one
+// copy per row it is responsible for, all of them complete on the warp's mbarrier,
+// so a warp has the whole piece (up to kStageBytes) in flight at once without
+// holding a single row in registers.  The groups of the warp then add the staged
+// rows in a fixed order.
+constexpr int kLongWarps = 12;                 // warps per CTA (one stage buffer each)
+constexpr int kStageBytes = 16384;             // bytes of rows staged per warp
+constexpr int kMaxPiece = 256;                 // rows per piece at most (scale buffer)
+
+static inline int piece_rows(int dim) {
+  int p = kStageBytes / (dim * 4);
+  if (p > kMaxPiece) p = kMaxPiece;
+  if (p < 4) p = 4;
+  return p;
+}
+
 template <int V, int OPT, int MODE, bool FAST>
-__global__ void __launch_bounds__(kUpdThreads, (V == 1 ? 2 : 1))
+__global__ void __launch_bounds__(kLongWarps * 32, 1)
 update_long_kernel(const __grid_constant__ UpdParams P) {
-  constexpr int kBatch = (V == 1) ? 8 : (V == 2 ? 4 : 2);  // gradient rows in flight per group
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  __shared__ uint64_t s_bar[kLongWarps];
+  constexpr int kBatch = (V == 1) ? 8 : (V == 2 ? 4 : 2);  // partial rows in flight (final combine)
   const unsigned lane = lane_id();
-  const int warps_per_cta = kUpdThreads / 32;
+  const int warp = threadIdx.x >> 5;
+  float* stage = reinterpret_cast<float*>(s_dyn + (size_t)warp * kStageBytes);
+  float* s_scale = reinterpret_cast<float*>(s_dyn + (size_t)kLongWarps * kStageBytes) + warp * kMaxPiece;
+  uint64_t* bar = &s_bar[warp];
+  if (lane == 0) mbar_init(bar, 1);
+  mbar_init_fence();
+  __syncthreads();
+  uint32_t parity = 0;
   int total = P.long_count[0];
   if (total > P.item_cap) total = P.item_cap;
   bool oob = false;
-  for (int it = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); it < total;
-       it += gridDim.x * warps_per_cta) {
+  for (int it = blockIdx.x * kLongWarps + warp; it < total; it += gridDim.x * kLongWarps) {
     const LongItem item = P.items[it];
     const UpdFeat& F = P.f[item.feat];
     const int log2g = F.log2g;
@@ -546,6 +581,7 @@ update_long_kernel(const __grid_constant__ UpdParams P) {
     const int gi = lane >> log2g;
     const int l = lane & (G - 1);
     const int dim = F.dim;
+    const uint32_t row_bytes = (uint32_t)dim * 4u;
     const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
     int col[V];
     bool act[V];
@@ -556,49 +592,41 @@ update_long_kernel(const __grid_constant__ UpdParams P) {
     }
     const int rs = F.ustart[item.u];
     const int re = F.ustart[item.u + 1];
-    const int np = (re - rs + kPiece - 1) / kPiece;
-    const int s = rs + item.piece * kPiece;
-    const int m = min(kPiece, re - s);
+    const int np = (re - rs + F.piece - 1) / F.piece;
+    const int s = rs + item.piece * F.piece;
+    const int m = min(F.piece, re - s);
     const uint32_t key = F.ukey[item.u];
-    // group gi sums entries gi, gi + ng, gi + 2 ng, ... of the piece, in that order
+    // stage the piece: lane j, j + 32, ... each start the bulk copy of one row
+    fence_proxy_async();   // the previous item's reads of the buffer are done (generic -> async)
+    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)m * row_bytes);
+    __syncwarp();
+    for (int j = (int)lane; j < m; j += 32) {
+      const int bag = entry_bag(F, s + j);
+      bulk_g2s(stage + (size_t)j * dim, F.grad + (int64_t)bag * F.grad_stride, row_bytes, bar);
+      if (scaled) s_scale[j] = bag_scale(F, bag);
+    }
+    __syncwarp();
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    // group gi adds rows gi, gi + ng, gi + 2 ng, ... of the piece, in that order
     float4 acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = f4_zero();
     bool first = true;
-    for (int j0 = 0; j0 < m; j0 += ng * kBatch) {  // warp-uniform trip count
-      int bag[kBatch];
+    for (int j = gi; j < m; j += ng) {
+      const float c = scaled ? s_scale[j] : 1.0f;
 #pragma unroll
-      for (int i = 0; i < kBatch; ++i) {
-        const int j = j0 + i * ng + gi;
-        bag[i] = j < m ? entry_bag(F, s + j) : -1;
-      }
-      float4 x[kBatch][V];
-      float c[kBatch];
-#pragma unroll
-      for (int i = 0; i < kBatch; ++i) {
-        c[i] = 1.0f;
-        if (scaled && bag[i] >= 0) c[i] = bag_scale(F, bag[i]);
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          x[i][v] = f4_zero();
-          if (bag[i] >= 0 && act[v])
-            x[i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
-                F.grad + (int64_t)bag[i] * F.grad_stride + col[v]));
+      for (int v = 0; v < V; ++v)
+        if (act[v]) {
+          float4 t = *reinterpret_cast<const float4*>(stage + (size_t)j * dim + col[v]);
+          if (scaled) t = f4_div_rn(t, c);
+          acc[v] = first ? t : f4_add_rn(acc[v], t);
         }
-      }
-#pragma unroll
-      for (int i = 0; i < kBatch; ++i)
-        if (bag[i] >= 0) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            const float4 t = scaled ? f4_div_rn(x[i][v], c[i]) : x[i][v];
-            acc[v] = first ? t : f4_add_rn(acc[v], t);
-          }
-          first = false;
-        }
+      first = false;
     }
+    __syncwarp();
     // group sums -> piece sum, fixed order: g0 += g(ng/2) ... (groups beyond the
-    // piece hold zeros; m >= ng is not required)
+    // piece hold zeros)
 #pragma unroll
     for (int v = 0; v < V; ++v)
       for (int off = ng >> 1; off >= 1; off >>= 1) {
@@ -628,29 +656,40 @@ update_long_kernel(const __grid_constant__ UpdParams P) {
     old = __shfl_sync(0xffffffffu, old, 0);
     if (old != np - 1) continue;  // warp-uniform
     __threadfence();
-    if (gi == 0) {
-      const float* p0 = P.part + (size_t)item.pbase * P.part_stride;
-      float4 tot[V];
+    // group gi adds pieces gi, gi + ng, ...; the group sums are combined as above
+    const float* p0 = P.part + (size_t)item.pbase * P.part_stride;
+    float4 tot[V];
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-        tot[v] = act[v] ? ld_cg_f4(reinterpret_cast<const float4*>(p0 + col[v])) : f4_zero();
-      for (int j0 = 1; j0 < np; j0 += kBatch) {
-        float4 x[kBatch][V];
+    for (int v = 0; v < V; ++v) tot[v] = f4_zero();
+    bool first2 = true;
+    for (int j0 = gi; j0 < np; j0 += ng * kBatch) {  // warp-uniform trip count
+      float4 x[kBatch][V];
 #pragma unroll
-        for (int i = 0; i < kBatch; ++i)
+      for (int i = 0; i < kBatch; ++i)
 #pragma unroll
-          for (int v = 0; v < V; ++v)
-            x[i][v] = (j0 + i < np && act[v])
-                          ? ld_cg_f4(reinterpret_cast<const float4*>(p0 + (size_t)(j0 + i) * P.part_stride + col[v]))
-                          : f4_zero();
+        for (int v = 0; v < V; ++v)
+          x[i][v] = (j0 + i * ng < np && act[v])
+                        ? ld_cg_f4(reinterpret_cast<const float4*>(p0 + (size_t)(j0 + i * ng) * P.part_stride + col[v]))
+                        : f4_zero();
 #pragma unroll
-        for (int i = 0; i < kBatch; ++i)
-          if (j0 + i < np)
+      for (int i = 0; i < kBatch; ++i)
+        if (j0 + i * ng < np) {
 #pragma unroll
-            for (int v = 0; v < V; ++v) tot[v] = f4_add_rn(tot[v], x[i][v]);
-      }
-      sink_row<V, OPT, MODE, FAST>(P, F, key, item.u, tot, col, act, oob);
+          for (int v = 0; v < V; ++v) tot[v] = first2 ? x[i][v] : f4_add_rn(tot[v], x[i][v]);
+          first2 = false;
+        }
     }
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      for (int off = ng >> 1; off >= 1; off >>= 1) {
+        float4 y;
+        y.x = __shfl_down_sync(0xffffffffu, tot[v].x, off << log2g);
+        y.y = __shfl_down_sync(0xffffffffu, tot[v].y, off << log2g);
+        y.z = __shfl_down_sync(0xffffffffu, tot[v].z, off << log2g);
+        y.w = __shfl_down_sync(0xffffffffu, tot[v].w, off << log2g);
+        if (gi < off) tot[v] = f4_add_rn(tot[v], y);
+      }
+    if (gi == 0) sink_row<V, OPT, MODE, FAST>(P, F, key, item.u, tot, col, act, oob);
   }
   if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
 }
@@ -703,7 +742,7 @@ constexpr int kRadixBins = 1 << kRadixBits;
 
 // per-feature workspace layout (a function of nnz, dim and offsets != NULL only)
 struct UpdLayout {
-  size_t keysA, keysB, valsA, valsB, bagmap, ukey, ustart, counts, end;
+  size_t keysA, keysB, valsA, valsB, bagmap, ukey, ustart, uval, counts, end;
   int log2g, V;
 };
 
@@ -717,6 +756,7 @@ static UpdLayout upd_layout(const hbUpdateFeature& f, size_t base) {
   L.bagmap = take(f.offsets ? 4 * n : 0);
   L.ukey = take(4 * n);
   L.ustart = take(4 * (n + 1));
+  L.uval = take(4 * n);
   L.counts = take(64);
   upd_shape(f.dim, &L.log2g, &L.V);
   L.end = o;
@@ -734,17 +774,26 @@ struct SharedLayout {
   int item_cap, part_cap, part_stride;
 };
 
-static SharedLayout shared_layout(size_t base, int nc, size_t total_tiles, size_t total_nnz, int max_dim) {
+// Queue bounds of one feature: every queued run is longer than kShortMax, so there are
+// fewer than nnz / kShortMax of them, each with at most len / piece + 1 pieces; only
+// runs of more than one piece (len > piece) park partial sums.
+static inline size_t long_items_of(int64_t nnz, int dim) {
+  return (size_t)(nnz / kShortMax + nnz / piece_rows(dim) + 2);
+}
+static inline size_t long_parts_of(int64_t nnz, int dim) { return (size_t)(2 * (nnz / piece_rows(dim)) + 2); }
+
+static SharedLayout shared_layout(size_t base, int nc, size_t total_tiles, size_t run_tiles,
+                                  size_t item_cap, size_t part_cap, int max_dim) {
   SharedLayout S;
   size_t o = align_up(base, 256);
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
   S.zero_sort = o;
   S.bucket = take(bucket_scratch_words(nc, total_tiles, kRadixBins, kMaxPasses) * sizeof(uint32_t));
-  S.run_status = take((total_tiles + (size_t)nc + 1) * sizeof(uint32_t));
+  S.run_status = take((run_tiles + (size_t)nc + 1) * sizeof(uint32_t));
   S.run_ticket = take(64);
   S.zero_sort_bytes = o - S.zero_sort;
-  S.item_cap = (int)(total_nnz / 8 + 4 * (size_t)nc + 64);
-  S.part_cap = (int)(total_nnz / 128 + 4 * (size_t)nc + 64);
+  S.item_cap = (int)item_cap;
+  S.part_cap = (int)part_cap;
   S.part_stride = (max_dim + 3) / 4 * 4;
   S.zero_apply = o;
   S.long_count = take(64);
@@ -755,6 +804,8 @@ static SharedLayout shared_layout(size_t base, int nc, size_t total_tiles, size_
   S.end = o;
   return S;
 }
+
+static inline size_t run_tiles_of(int64_t nnz) { return (size_t)((nnz + kRunTile - 1) / kRunTile) + 1; }
 
 template <int V, int OPT, int MODE, bool FAST>
 static int launch_apply(const UpdParams& U, int max_short_ctas, cudaStream_t stream) {
@@ -771,15 +822,15 @@ static int launch_apply(const UpdParams& U, int max_short_ctas, cudaStream_t str
     HB_CUDA_OK(cudaGetLastError());
   }
   {
-    int per_sm = 0;
-    HB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &per_sm, update_long_kernel<V, OPT, MODE, FAST>, kUpdThreads, 0));
-    int grid = sms * (per_sm > 0 ? per_sm : 1);
-    const int need = (U.item_cap + kUpdThreads / 32 - 1) / (kUpdThreads / 32);
+    const size_t smem = (size_t)kLongWarps * kStageBytes + (size_t)kLongWarps * kMaxPiece * sizeof(float);
+    HB_CUDA_OK(cudaFuncSetAttribute(update_long_kernel<V, OPT, MODE, FAST>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = sms;  // one CTA of kLongWarps stage buffers per SM
+    const int need = (U.item_cap + kLongWarps - 1) / kLongWarps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     KernelScope ks(HB_K_UPDATE_LONG, stream);
-    update_long_kernel<V, OPT, MODE, FAST><<<grid, kUpdThreads, 0, stream>>>(U);
+    update_long_kernel<V, OPT, MODE, FAST><<<grid, kLongWarps * 32, smem, stream>>>(U);
     HB_CUDA_OK(cudaGetLastError());
   }
   return HB_OK;
@@ -858,16 +909,18 @@ size_t sparse_update_workspace_bytes(int n, const hbUpdateFeature* feats) {
   size_t o = 0, max_shared = 0;
   for (int c0 = 0; c0 < n; c0 += kMaxUpdFeats) {
     const int nc = (n - c0 < kMaxUpdFeats) ? n - c0 : kMaxUpdFeats;
-    size_t tiles = 0, nnz = 0;
+    size_t tiles = 0, rtiles = 0, items = 64, parts = 64;
     int max_dim = 4;
     for (int k = 0; k < nc; ++k) {
       const hbUpdateFeature& f = feats[c0 + k];
       o = upd_layout(f, o).end;
       tiles += bucket_tiles(f.nnz);
-      nnz += (size_t)f.nnz;
+      rtiles += run_tiles_of(f.nnz);
+      items += long_items_of(f.nnz, f.dim);
+      parts += long_parts_of(f.nnz, f.dim);
       if (f.dim > max_dim) max_dim = f.dim;
     }
-    const size_t sb = shared_layout(0, nc, tiles, nnz, max_dim).end;
+    const size_t sb = shared_layout(0, nc, tiles, rtiles, items, parts, max_dim).end;
     if (sb > max_shared) max_shared = sb;
   }
   return align_up(o, 256) + max_shared + 256;
@@ -906,7 +959,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
     UpdLayout L[kMaxUpdFeats];
     int passes[kMaxUpdFeats];
     size_t o = off;
-    size_t total_tiles = 0, total_nnz = 0;
+    size_t total_tiles = 0, total_rtiles = 0, total_items = 64, total_parts = 64;
     int max_passes = 0, max_dim = 4;
     for (int k = 0; k < nc; ++k) {
       const hbUpdateFeature& f = feats[c0 + k];
@@ -914,7 +967,9 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
       L[k] = upd_layout(f, o);
       o = L[k].end;
       total_tiles += (size_t)bucket_tiles(f.nnz);
-      total_nnz += (size_t)f.nnz;
+      total_rtiles += run_tiles_of(f.nnz);
+      total_items += long_items_of(f.nnz, f.dim);
+      total_parts += long_parts_of(f.nnz, f.dim);
       if (f.dim > max_dim) max_dim = f.dim;
       int64_t space = f.rows;
       if (ex && ex->key_kind == 1) space = (int64_t)feats[0].id_div << ex->lbits;
@@ -928,7 +983,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
       }
     }
     off = o;
-    const SharedLayout S = shared_layout(feat_end, nc, total_tiles, total_nnz, max_dim);
+    const SharedLayout S = shared_layout(feat_end, nc, total_tiles, total_rtiles, total_items, total_parts, max_dim);
 
     if (phases & kPhaseSort) {
       // 1. bag map for CSR features
@@ -1043,13 +1098,14 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         F.vals = reinterpret_cast<int32_t*>(base + (inA ? L[k].valsA : L[k].valsB));
         F.ukey = reinterpret_cast<uint32_t*>(base + L[k].ukey);
         F.ustart = reinterpret_cast<int32_t*>(base + L[k].ustart);
+        F.uval = reinterpret_cast<int32_t*>(base + L[k].uval);
         F.counts = reinterpret_cast<int32_t*>(base + L[k].counts);
         F.inv = ex ? ex->inv : nullptr;
         F.owner_start1 = ex ? ex->owner_start1 : nullptr;
         F.n_dev = ex ? ex->n_dev : nullptr;
         F.n = (int32_t)f.nnz;
         F.lbits = ex ? ex->lbits : 0;
-        static_tiles += (size_t)((f.nnz + kRunTile - 1) / kRunTile) + 1;
+        static_tiles += run_tiles_of(f.nnz);
       }
       const int maxg = device_sm_count() * 4;
       const int grid = static_tiles < (size_t)maxg ? (int)static_tiles : maxg;
@@ -1094,6 +1150,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         F.ukey = reinterpret_cast<uint32_t*>(base + L[k].ukey);
         F.ustart = reinterpret_cast<int32_t*>(base + L[k].ustart);
         F.counts = reinterpret_cast<int32_t*>(base + L[k].counts);
+        F.uval = reinterpret_cast<int32_t*>(base + L[k].uval);
         F.vals = reinterpret_cast<int32_t*>(base + (inA ? L[k].valsA : L[k].valsB));
         F.pos2bag = (ex && ex->inv != nullptr && f.offsets != nullptr)
                         ? reinterpret_cast<const int32_t*>(base + L[k].bagmap) : nullptr;
@@ -1106,6 +1163,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         F.log2g = L[k].log2g;
         const int uc = (kUpdThreads >> L[k].log2g) * kNU;
         F.max_chunks = (int)((f.nnz + uc - 1) / uc);
+        F.piece = piece_rows(f.dim);
         max_ctas += F.max_chunks;
         U.nfeats++;
       }

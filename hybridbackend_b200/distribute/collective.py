@@ -28,7 +28,7 @@ class _AlltoallFn(torch.autograd.Function):
 
   @staticmethod
   def backward(ctx, grad):
-    return None, ctx.coll._alltoall_equal([grad.contiguous()])[0]
+    return None, ctx.coll.alltoall_grad(grad)
 
 
 class _AlltoallvFn(torch.autograd.Function):
@@ -48,9 +48,7 @@ class _AlltoallvFn(torch.autograd.Function):
   @staticmethod
   def backward(ctx, grad, _sizes_grad):
     (osz,) = ctx.saved_tensors
-    outs, _ = ctx.coll._alltoallv_n([grad.contiguous()], [osz],
-                                    None if ctx.common_shape is None else [ctx.common_shape])
-    return None, outs[0], None, None
+    return None, ctx.coll.alltoall_grad(grad, osz, ctx.common_shape), None, None
 
 
 class Topology:
@@ -214,6 +212,16 @@ class Collective:
     if single:
       return outs[0], osz[0]
     return outs, osz
+
+  def alltoall_grad(self, value_grad, exchanged_sizes=None, common_shape=None):
+    """Gradient of alltoall w.r.t. its `value` (collective.py:306-319, :334-348):
+    the upstream gradient shuffled back with the RECEIVED sizes.  This is what the
+    autograd form calls; exposed for graph builders that wire gradients themselves."""
+    if exchanged_sizes is None:
+      return self._alltoall_equal([value_grad.contiguous()])[0]
+    outs, _ = self._alltoallv_n([value_grad.contiguous()], [exchanged_sizes],
+                                None if common_shape is None else [common_shape])
+    return outs[0]
 
   def _alltoall_equal(self, values):
     W = self.world_size

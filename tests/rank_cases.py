@@ -121,34 +121,48 @@ def alltoallv_golden(env):
 
 def alltoallv_grads(env):
   """Gradient vectors of the reference: alltoall_test.py:207-217 (alltoall),
-  :228-243 (alltoallv), :288-304 (alltoallv_n): loss = mean(output), upstream g."""
+  :228-243 (alltoallv), :288-304 (alltoallv_n): loss = mean(output), upstream g.
+  With one process per rank the gradient flows through torch autograd
+  (_AlltoallvFn); with one THREAD per rank the backward is called directly
+  (Collective.alltoall_grad, the call autograd makes) because torch runs all CUDA
+  backward nodes of a device on one engine thread, where two ranks' collectives
+  cannot meet."""
   assert env.world == 2
   rank, dev = env.rank, env.device
   coll = env.collective(8 << 20)
   soft = Soft()
   g = 2.0
+
+  def grad_of(x, sizes):
+    if env.autograd:
+      x = x.clone().requires_grad_(True)
+      out = coll.alltoall(x, sizes=sizes)
+      out = out[0] if sizes is not None else out
+      (out.mean() * g).backward()
+      return x.grad
+    out = coll.alltoall(x, sizes=sizes)
+    out, osz = out if sizes is not None else (out, None)
+    dout = torch.full_like(out, g / out.numel())
+    return coll.alltoall_grad(dout, osz)
+
   # alltoallv_grad: sizes [[5,1],[3,4]]
   sizes = [[5, 1], [3, 4]]
   values = [3.6, 4.2]
-  x = torch.full((sum(sizes[rank]),), values[rank], device=dev, requires_grad=True)
-  out, _ = coll.alltoall(x, sizes=torch.tensor(sizes[rank], dtype=torch.int32, device=dev))
-  (out.mean() * g).backward()
+  x = torch.full((sum(sizes[rank]),), values[rank], device=dev)
+  got = grad_of(x, torch.tensor(sizes[rank], dtype=torch.int32, device=dev))
   g0 = g / (sizes[0][0] + sizes[1][0])
   g1 = g / (sizes[0][1] + sizes[1][1])
   exp = sizes[rank][0] * [g0] + sizes[rank][1] * [g1]
-  soft.allclose(x.grad.cpu().numpy(), np.asarray(exp, np.float32), 'alltoallv grad', rtol=1e-6)
+  soft.allclose(got.cpu().numpy(), np.asarray(exp, np.float32), 'alltoallv grad', rtol=1e-6)
   # alltoallv_n_grad: every gradient is g / 3
   inputs = {0: [([1., 2., 3.], [1, 2]), ([4., 5., 6.], [2, 1])],
             1: [([7., 8., 9.], [2, 1]), ([10., 11., 12.], [1, 2])]}
   for v, s in inputs[rank]:
-    x = torch.tensor(v, device=dev, requires_grad=True)
-    out, _ = coll.alltoall(x, sizes=torch.tensor(s, dtype=torch.int32, device=dev))
-    (out.mean() * g).backward()
-    soft.allclose(x.grad.cpu().numpy(), np.full(3, g / 3, np.float32), 'alltoallv_n grad', rtol=1e-6)
+    got = grad_of(torch.tensor(v, device=dev), torch.tensor(s, dtype=torch.int32, device=dev))
+    soft.allclose(got.cpu().numpy(), np.full(3, g / 3, np.float32), 'alltoallv_n grad', rtol=1e-6)
   # alltoall_grad (equal split, [w, h] = [2, 10]): g / (w * h) everywhere
-  x = torch.randn(2, 10, device=dev, requires_grad=True)
-  (coll.alltoall(x).mean() * g).backward()
-  soft.allclose(x.grad.cpu().numpy(), np.full((2, 10), g / 20, np.float32), 'alltoall grad', rtol=1e-6)
+  got = grad_of(torch.randn(2, 10, device=dev), None)
+  soft.allclose(got.cpu().numpy(), np.full((2, 10), g / 20, np.float32), 'alltoall grad', rtol=1e-6)
   torch.cuda.synchronize()
   env.barrier()
   coll.close()

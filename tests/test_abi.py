@@ -35,7 +35,7 @@ def test_partition_workspace_query_and_validation(hb):
   need = C.c_size_t(0)
   lens = (C.c_int32 * 3)(65536, 0, 5)
   assert L.hbPartitionWorkspaceBytes(3, lens, 8, C.byref(need)) == 0
-  assert need.value >= (32 + 0 + 1) * 8 * 4
+  assert need.value >= (16 + 0 + 1) * 8 * 4   # one status row of 8 bins per 4096-id tile
   bad = (C.c_int32 * 1)(-1)
   assert L.hbPartitionWorkspaceBytes(1, bad, 8, C.byref(need)) != 0
   assert b'negative' in L.hbGetLastErrorString()

@@ -33,6 +33,7 @@ class LocalEnv:
     self.rank, self.world = rank, world
     self.device = torch.device('cuda', 0)
     self.hb, self.oracle = hb, oracle
+    self.autograd = False
     self._shared = shared
     self._ncoll = 0
 

@@ -28,6 +28,7 @@ class ProcEnv:
     self.rank, self.world = rank, world
     self.device = torch.device('cuda', rank)
     self.hb, self.oracle = hb, oracle
+    self.autograd = True
 
   def collective(self, window_bytes):
     return self.hb.distribute.Collective(self.rank, self.world, window_bytes=window_bytes,
