@@ -333,8 +333,10 @@ def run_ours(args):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host = time.perf_counter()
     for i in range(steps):
       step(i, host)
+    timed.host_ms = (time.perf_counter() - t_host) * 1e3 / steps  # host enqueue time per step
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -360,6 +362,7 @@ def run_ours(args):
     clocks.lines.clear()   # keep only samples taken from here on (timed region under load)
   l0 = L.hbGetLaunchCount()
   ms = timed(K)
+  host_ms = timed.host_ms
   launches = L.hbGetLaunchCount() - l0
   # the timed region is only tens of ms: keep the GPUs under the same load for
   # ~0.5 s more (same step count on every rank) so the 100 ms sampler sees it
@@ -476,7 +479,7 @@ def run_ours(args):
         'n_gpus': world, 'steps': K, 'warmup': W_, 'ms_per_step': ms / K, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, dim, sizes), 'clocks': clk, 'e2e': e2e,
-        'gpu_launches': int(launches), 'roofline': roofline, 'roofline_all': roofs,
+        'gpu_launches': int(launches), 'host_enqueue_ms_per_step': host_ms, 'roofline': roofline, 'roofline_all': roofs,
         'kernels': kern, 'cpu_baseline': cpu,
         'roofline_note': 'per-kernel CUDA events recorded by the library on the launching stream in '
                          'a second pass of the same K steps (hbProfileEnable), single stream (no fwd/sort overlap)',

@@ -60,11 +60,17 @@ struct UpdFeat {
   int32_t dim;
   int32_t combiner;
   int32_t log2g;
-  int32_t max_chunks;       // static bound of the number of chunks of this feature
+  int32_t max_chunks;       // static bound of the number of warp units of this feature (0: not in this launch)
   int32_t piece;            // entries per piece of a long run (kStageBytes of rows)
 };
 
-struct LongItem { int32_t feat, u, piece, pbase; };
+struct LongItem {   // one piece of a hot row
+  int32_t feat, u;
+  int32_t start, count;   // sorted entries [start, start + count)
+  uint32_t key;
+  int32_t pbase;          // first partial slot of the run (-1: single piece)
+  int32_t piece, np;
+};
 
 struct UpdParams {
   UpdFeat f[kMaxUpdFeats];
@@ -76,6 +82,7 @@ struct UpdParams {
   float* part;              // [part_cap][part_stride] piece sums of multi-piece runs
   int32_t* tickets;         // [part_cap] arrival counters, indexed by the run's pbase
   int32_t item_cap, part_cap, part_stride;
+  int32_t ticket_base;      // work tickets of this launch: long_count[ticket_base + {0: pieces, 1: short units}]
   int32_t nfeats;
   int32_t opt;
   int32_t fast;             // approximate sqrt/div (MUFU) instead of the IEEE sequence
@@ -371,35 +378,120 @@ __global__ void __launch_bounds__(kUpdThreads) runs_kernel(const __grid_constant
   if (oob) raise_status(P.d_status, HB_STATUS_ID_OUT_OF_RANGE);
 }
 
-// ---- 4. short runs ----------------------------------------------------------------------
-__device__ __forceinline__ void queue_long(const UpdParams& P, const UpdFeat& F, int fi, int u, int len) {
-  const int np = (len + F.piece - 1) / F.piece;
-  const int base = atomicAdd(&P.long_count[0], np);
-  const int pb = np > 1 ? atomicAdd(&P.long_count[1], np) : -1;
-  if (base + np > P.item_cap || (np > 1 && pb + np > P.part_cap)) {  // cannot happen by the layout bounds
-    raise_status(P.status, HB_STATUS_WINDOW_OVERFLOW);
-    return;
-  }
-  for (int j = 0; j < np; ++j) P.items[base + j] = LongItem{fi, u, j, pb};
+// ---- 4. queue of hot rows ---------------------------------------------------------------
+// Runs longer than kShortMax are cut into pieces of `piece` entries and queued; the
+// apply kernel gives every piece to one warp.  Part of the sort phase (needs ids only).
+constexpr int kStageBytes = 8192;              // bytes of gradient rows a warp stages per piece
+constexpr int kMaxPiece = 64;                  // rows per piece at most (two bag registers per lane)
+
+static inline int piece_rows(int dim) {
+  int p = kStageBytes / (dim * 4);
+  if (p > kMaxPiece) p = kMaxPiece;
+  if (p < 2) p = 2;
+  return p;
 }
 
-// run bounds, key and first value of the kNU unique rows a group owns in `chunk`
+struct QueueFeat {
+  const int32_t* ustart;
+  const uint32_t* ukey;
+  const int32_t* counts;
+  int32_t piece;
+  int32_t max_chunks;
+};
+struct QueueParams {
+  QueueFeat f[kMaxUpdFeats];
+  int32_t* long_count;   // [0] queued pieces, [1] reserved partial slots
+  LongItem* items;
+  int32_t* status;
+  int32_t item_cap, part_cap;
+  int32_t nfeats;
+};
+
+__global__ void __launch_bounds__(kUpdThreads) queue_kernel(const __grid_constant__ QueueParams P) {
+  __shared__ int s_begin[kMaxUpdFeats + 1];
+  int units = 0;
+  if ((int)threadIdx.x < P.nfeats) {
+    units = (P.f[threadIdx.x].counts[0] + kUpdThreads - 1) / kUpdThreads;
+    if (units > P.f[threadIdx.x].max_chunks) units = P.f[threadIdx.x].max_chunks;
+  }
+  const int total = seg_scan(P.nfeats, units, s_begin);
+  const unsigned lane = lane_id();
+  for (int chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+    const int fi = seg_find(s_begin, P.nfeats, chunk);
+    const QueueFeat& F = P.f[fi];
+    const int u = (chunk - s_begin[fi]) * kUpdThreads + (int)threadIdx.x;
+    int s = 0, len = 0;
+    if (u < F.counts[0]) {
+      s = F.ustart[u];
+      len = F.ustart[u + 1] - s;
+    }
+    const bool is_long = len > kShortMax;
+    const int np = is_long ? (len + F.piece - 1) / F.piece : 0;
+    int base = 0, pb = -1;
+    uint32_t key = 0;
+    if (is_long) {
+      base = atomicAdd(&P.long_count[0], np);
+      if (np > 1) pb = atomicAdd(&P.long_count[1], np);
+      key = F.ukey[u];
+      if (base + np > P.item_cap || (np > 1 && pb + np > P.part_cap)) {  // cannot happen by the layout bounds
+        raise_status(P.status, HB_STATUS_WINDOW_OVERFLOW);
+        base = -1;
+      }
+    }
+    // the pieces of a hot row are written by the whole warp (the hottest row of a
+    // power-law feature has hundreds of them)
+    unsigned todo = __ballot_sync(0xffffffffu, is_long && base >= 0);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int r_u = __shfl_sync(0xffffffffu, u, src);
+      const int r_s = __shfl_sync(0xffffffffu, s, src);
+      const int r_len = __shfl_sync(0xffffffffu, len, src);
+      const int r_np = __shfl_sync(0xffffffffu, np, src);
+      const int r_base = __shfl_sync(0xffffffffu, base, src);
+      const int r_pb = __shfl_sync(0xffffffffu, pb, src);
+      const uint32_t r_key = __shfl_sync(0xffffffffu, key, src);
+      for (int j = (int)lane; j < r_np; j += 32) {
+        LongItem it;
+        it.feat = fi; it.u = r_u; it.start = r_s + j * F.piece;
+        it.count = min(F.piece, r_len - j * F.piece);
+        it.key = r_key; it.pbase = r_pb; it.piece = j; it.np = r_np;
+        P.items[r_base + j] = it;
+      }
+    }
+  }
+}
+
+// ---- 5. apply: short runs and hot-row pieces in ONE launch ---------------------------------
+// Both kinds of work are chains of dependent memory round trips, so neither fills the
+// machine alone; warps of either kind share every SM.  The split of the warps between
+// the kinds is derived on the device from the amount of queued work.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+               :: "r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// run bounds, key and first value of the kNU unique rows a group owns in warp unit `unit`
 struct ShortMeta {
   int fi;
   int us[kNU], s[kNU], len[kNU], v0[kNU];
   uint32_t key[kNU];
 };
 
-__device__ __forceinline__ void short_meta(const UpdParams& P, const int* s_begin, int chunk, ShortMeta& M) {
-  M.fi = seg_find(s_begin, P.nfeats, chunk);
+__device__ __forceinline__ void short_meta(const UpdParams& P, const int* s_begin, int unit, unsigned lane,
+                                           ShortMeta& M) {
+  M.fi = seg_find(s_begin, P.nfeats, unit);
   const UpdFeat& F = P.f[M.fi];
-  const int groups = kUpdThreads >> F.log2g;
-  const int g = threadIdx.x >> F.log2g;
+  const int ng = 32 >> F.log2g;
+  const int gi = (int)lane >> F.log2g;
   const int U = F.counts[0];
-  const int u0 = (chunk - s_begin[M.fi]) * groups * kNU;
+  const int u0 = (unit - s_begin[M.fi]) * ng * kNU;
 #pragma unroll
-  for (int q = 0; q < kNU; ++q) {  // consecutive groups <-> consecutive uniques (coalesced)
-    M.us[q] = u0 + q * groups + g;
+  for (int q = 0; q < kNU; ++q) {  // consecutive groups <-> consecutive uniques
+    M.us[q] = u0 + q * ng + gi;
     const bool ok = M.us[q] < U;
     const int uu = ok ? M.us[q] : 0;
     M.s[q] = F.ustart[uu];
@@ -410,287 +502,336 @@ __device__ __forceinline__ void short_meta(const UpdParams& P, const int* s_begi
 }
 
 template <int V, int OPT, int MODE, bool FAST>
-__global__ void __launch_bounds__(kUpdThreads, (V == 1 ? 3 : (V == 2 ? 2 : 1)))
-update_short_kernel(const __grid_constant__ UpdParams P) {
-  __shared__ int s_begin[kMaxUpdFeats + 1];
-  wait_spec(P.wait, P.status);
-  const int tid = threadIdx.x;
-  int units = 0;
-  if (tid < P.nfeats) {
-    const int uc = (kUpdThreads >> P.f[tid].log2g) * kNU;
-    units = (P.f[tid].counts[0] + uc - 1) / uc;
-    if (units > P.f[tid].max_chunks) units = P.f[tid].max_chunks;
+__device__ __forceinline__ void short_unit(const UpdParams& P, ShortMeta& M, unsigned lane, bool& oob) {
+  const UpdFeat& F = P.f[M.fi];
+  const int log2g = F.log2g;
+  const int l = (int)lane & ((1 << log2g) - 1);
+  const int dim = F.dim;
+  const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
+  int col[V];
+  bool act[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    col[v] = ((v << log2g) + l) * 4;
+    act[v] = col[v] < dim;
   }
-  const int total = seg_scan(P.nfeats, units, s_begin);
-  bool oob = false;
-  int chunk = blockIdx.x;
-  ShortMeta M, Mn;
-  if (chunk < total) short_meta(P, s_begin, chunk, M);
-  while (chunk < total) {
-    // the NEXT chunk's run bounds travel while this chunk's rows do
-    const int next = chunk + gridDim.x;
-    if (next < total) short_meta(P, s_begin, next, Mn);
-    const UpdFeat& F = P.f[M.fi];
-    const int log2g = F.log2g;
-    const int l = tid & ((1 << log2g) - 1);
-    const int dim = F.dim;
-    const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
-    int col[V];
-    bool act[V];
+  bool ok[kNU];
+#pragma unroll
+  for (int q = 0; q < kNU; ++q) {
+    ok[q] = M.len[q] > 0 && M.len[q] <= kShortMax;  // longer runs are queued pieces
+    if (MODE == kModeApply && ok[q] && (uint64_t)M.key[q] >= (uint64_t)F.rows) {
+      oob = true;
+      ok[q] = false;
+    }
+    if (!ok[q]) M.len[q] = 0;
+  }
+  // one round trip: table row, slot rows, the gradient row of the run's first entry (its
+  // bag came with the run bounds) and the bags of entries 1..3
+  float4 w[kNU][V], s0[kNU][V], s1[kNU][V], acc[kNU][V];
+  float sc0[kNU];
+  int b1[kNU][3];
+#pragma unroll
+  for (int q = 0; q < kNU; ++q) {
+    int bag0 = M.v0[q];
+    if (ok[q] && F.pos2bag != nullptr) bag0 = F.pos2bag[bag0];
+    sc0[q] = (scaled && ok[q]) ? bag_scale(F, bag0) : 1.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) b1[q][i] = (1 + i < M.len[q]) ? entry_bag(F, M.s[q] + 1 + i) : -1;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      col[v] = ((v << log2g) + l) * 4;
-      act[v] = col[v] < dim;
-    }
-    bool ok[kNU];
-#pragma unroll
-    for (int q = 0; q < kNU; ++q) {
-      ok[q] = M.len[q] > 0;
-      if (ok[q] && M.len[q] > kShortMax) {  // hot row: the long kernel sums it with whole warps
-        if (l == 0) queue_long(P, F, M.fi, M.us[q], M.len[q]);
-        ok[q] = false;
-      }
-      if (MODE == kModeApply && ok[q] && (uint64_t)M.key[q] >= (uint64_t)F.rows) {
-        oob = true;
-        ok[q] = false;
-      }
-      if (!ok[q]) M.len[q] = 0;
-    }
-    // one round trip: table row, slot rows and the gradient row of the run's first
-    // entry (its bag came with the run bounds)
-    float4 w[kNU][V], s0[kNU][V], s1[kNU][V], acc[kNU][V];
-    float sc0[kNU];
-#pragma unroll
-    for (int q = 0; q < kNU; ++q) {
-      int bag0 = M.v0[q];
-      if (ok[q] && F.pos2bag != nullptr) bag0 = F.pos2bag[bag0];
-      sc0[q] = (scaled && ok[q]) ? bag_scale(F, bag0) : 1.0f;
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        w[q][v] = s0[q][v] = s1[q][v] = acc[q][v] = f4_zero();
-        if (ok[q] && act[v]) {
-          acc[q][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.grad + (int64_t)bag0 * F.grad_stride + col[v]));
-          if constexpr (MODE == kModeApply) {
-            const int64_t o = (int64_t)M.key[q] * dim + col[v];
-            w[q][v] = *reinterpret_cast<const float4*>(F.table + o);
-            if constexpr (OPT != HB_OPT_SGD) s0[q][v] = *reinterpret_cast<const float4*>(F.slot0 + o);
-            if constexpr (OPT == HB_OPT_LAZY_ADAM) s1[q][v] = *reinterpret_cast<const float4*>(F.slot1 + o);
-          }
+      w[q][v] = s0[q][v] = s1[q][v] = acc[q][v] = f4_zero();
+      if (ok[q] && act[v]) {
+        acc[q][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.grad + (int64_t)bag0 * F.grad_stride + col[v]));
+        if constexpr (MODE == kModeApply) {
+          const int64_t o = (int64_t)M.key[q] * dim + col[v];
+          w[q][v] = *reinterpret_cast<const float4*>(F.table + o);
+          if constexpr (OPT != HB_OPT_SGD) s0[q][v] = *reinterpret_cast<const float4*>(F.slot0 + o);
+          if constexpr (OPT == HB_OPT_LAZY_ADAM) s1[q][v] = *reinterpret_cast<const float4*>(F.slot1 + o);
         }
       }
     }
-#pragma unroll
-    for (int q = 0; q < kNU; ++q) {
-      if (scaled) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) acc[q][v] = f4_div_rn(acc[q][v], sc0[q]);
-      }
-      // entries 1 .. len-1, four at a time, added in position order
-      for (int j0 = 1; j0 < M.len[q]; j0 += 4) {
-        int b4[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) b4[i] = (j0 + i < M.len[q]) ? entry_bag(F, M.s[q] + j0 + i) : -1;
-        float4 x[4][V];
-        float c4[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          c4[i] = 1.0f;
-          if (scaled && b4[i] >= 0) c4[i] = bag_scale(F, b4[i]);
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            x[i][v] = f4_zero();
-            if (b4[i] >= 0 && act[v])
-              x[i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
-                  F.grad + (int64_t)b4[i] * F.grad_stride + col[v]));
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (b4[i] >= 0)
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-              acc[q][v] = f4_add_rn(acc[q][v], scaled ? f4_div_rn(x[i][v], c4[i]) : x[i][v]);
-      }
-    }
-    // sink
-#pragma unroll
-    for (int q = 0; q < kNU; ++q) {
-      if (!ok[q]) continue;
-      if constexpr (MODE == kModeApply) {
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-          if (act[v]) {
-            const int64_t o = (int64_t)M.key[q] * dim + col[v];
-            opt_step4<OPT, FAST>(P, w[q][v], s0[q][v], s1[q][v], acc[q][v]);
-            *reinterpret_cast<float4*>(F.table + o) = w[q][v];
-            if constexpr (OPT != HB_OPT_SGD) *reinterpret_cast<float4*>(F.slot0 + o) = s0[q][v];
-            if constexpr (OPT == HB_OPT_LAZY_ADAM) *reinterpret_cast<float4*>(F.slot1 + o) = s1[q][v];
-          }
-      } else {
-        sink_row<V, OPT, MODE, FAST>(P, F, M.key[q], M.us[q], acc[q], col, act, oob);
-      }
-    }
-    M = Mn;
-    chunk = next;
   }
-  if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
-}
-
-// ---- 5. long runs -----------------------------------------------------------------------
-// One warp per piece.  The piece's gradient rows are STAGED in shared memory by 1-D
-// bulk asynchronous copies (cp.async.bulk, the TMA engine): every lane issues one
-// copy per row it is responsible for, all of them complete on the warp's mbarrier,
-// so a warp has the whole piece (up to kStageBytes) in flight at once without
-// holding a single row in registers.  The groups of the warp then add the staged
-// rows in a fixed order.
-constexpr int kLongWarps = 12;                 // warps per CTA (one stage buffer each)
-constexpr int kStageBytes = 16384;             // bytes of rows staged per warp
-constexpr int kMaxPiece = 256;                 // rows per piece at most (scale buffer)
-
-static inline int piece_rows(int dim) {
-  int p = kStageBytes / (dim * 4);
-  if (p > kMaxPiece) p = kMaxPiece;
-  if (p < 4) p = 4;
-  return p;
-}
-
-template <int V, int OPT, int MODE, bool FAST>
-__global__ void __launch_bounds__(kLongWarps * 32, 1)
-update_long_kernel(const __grid_constant__ UpdParams P) {
-  extern __shared__ __align__(128) unsigned char s_dyn[];
-  __shared__ uint64_t s_bar[kLongWarps];
-  constexpr int kBatch = (V == 1) ? 8 : (V == 2 ? 4 : 2);  // partial rows in flight (final combine)
-  const unsigned lane = lane_id();
-  const int warp = threadIdx.x >> 5;
-  float* stage = reinterpret_cast<float*>(s_dyn + (size_t)warp * kStageBytes);
-  float* s_scale = reinterpret_cast<float*>(s_dyn + (size_t)kLongWarps * kStageBytes) + warp * kMaxPiece;
-  uint64_t* bar = &s_bar[warp];
-  if (lane == 0) mbar_init(bar, 1);
-  mbar_init_fence();
-  __syncthreads();
-  uint32_t parity = 0;
-  int total = P.long_count[0];
-  if (total > P.item_cap) total = P.item_cap;
-  bool oob = false;
-  for (int it = blockIdx.x * kLongWarps + warp; it < total; it += gridDim.x * kLongWarps) {
-    const LongItem item = P.items[it];
-    const UpdFeat& F = P.f[item.feat];
-    const int log2g = F.log2g;
-    const int G = 1 << log2g;
-    const int ng = 32 >> log2g;        // groups per warp
-    const int gi = lane >> log2g;
-    const int l = lane & (G - 1);
-    const int dim = F.dim;
-    const uint32_t row_bytes = (uint32_t)dim * 4u;
-    const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
-    int col[V];
-    bool act[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      col[v] = ((v << log2g) + l) * 4;
-      act[v] = col[v] < dim;
-    }
-    const int rs = F.ustart[item.u];
-    const int re = F.ustart[item.u + 1];
-    const int np = (re - rs + F.piece - 1) / F.piece;
-    const int s = rs + item.piece * F.piece;
-    const int m = min(F.piece, re - s);
-    const uint32_t key = F.ukey[item.u];
-    // stage the piece: lane j, j + 32, ... each start the bulk copy of one row
-    fence_proxy_async();   // the previous item's reads of the buffer are done (generic -> async)
-    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)m * row_bytes);
-    __syncwarp();
-    for (int j = (int)lane; j < m; j += 32) {
-      const int bag = entry_bag(F, s + j);
-      bulk_g2s(stage + (size_t)j * dim, F.grad + (int64_t)bag * F.grad_stride, row_bytes, bar);
-      if (scaled) s_scale[j] = bag_scale(F, bag);
-    }
-    __syncwarp();
-    mbar_wait(bar, parity);
-    parity ^= 1u;
-    // group gi adds rows gi, gi + ng, gi + 2 ng, ... of the piece, in that order
-    float4 acc[V];
+  for (int q = 0; q < kNU; ++q) {
+    if (scaled) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = f4_zero();
-    bool first = true;
-    for (int j = gi; j < m; j += ng) {
-      const float c = scaled ? s_scale[j] : 1.0f;
+      for (int v = 0; v < V; ++v) acc[q][v] = f4_div_rn(acc[q][v], sc0[q]);
+    }
+    if (M.len[q] > 1) {
+      // entries 1..3 (bags already here), then 4.. in fours; added in position order
+      float4 x[3][V];
+      float c3[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        c3[i] = (scaled && b1[q][i] >= 0) ? bag_scale(F, b1[q][i]) : 1.0f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          x[i][v] = f4_zero();
+          if (b1[q][i] >= 0 && act[v])
+            x[i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
+                F.grad + (int64_t)b1[q][i] * F.grad_stride + col[v]));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (b1[q][i] >= 0)
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            acc[q][v] = f4_add_rn(acc[q][v], scaled ? f4_div_rn(x[i][v], c3[i]) : x[i][v]);
+    }
+    for (int j0 = 4; j0 < M.len[q]; j0 += 4) {
+      int b4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b4[i] = (j0 + i < M.len[q]) ? entry_bag(F, M.s[q] + j0 + i) : -1;
+      float4 x[4][V];
+      float c4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        c4[i] = (scaled && b4[i] >= 0) ? bag_scale(F, b4[i]) : 1.0f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          x[i][v] = f4_zero();
+          if (b4[i] >= 0 && act[v])
+            x[i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
+                F.grad + (int64_t)b4[i] * F.grad_stride + col[v]));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (b4[i] >= 0)
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            acc[q][v] = f4_add_rn(acc[q][v], scaled ? f4_div_rn(x[i][v], c4[i]) : x[i][v]);
+    }
+  }
+  // sink
+#pragma unroll
+  for (int q = 0; q < kNU; ++q) {
+    if (!ok[q]) continue;
+    if constexpr (MODE == kModeApply) {
 #pragma unroll
       for (int v = 0; v < V; ++v)
         if (act[v]) {
-          float4 t = *reinterpret_cast<const float4*>(stage + (size_t)j * dim + col[v]);
-          if (scaled) t = f4_div_rn(t, c);
-          acc[v] = first ? t : f4_add_rn(acc[v], t);
+          const int64_t o = (int64_t)M.key[q] * dim + col[v];
+          opt_step4<OPT, FAST>(P, w[q][v], s0[q][v], s1[q][v], acc[q][v]);
+          *reinterpret_cast<float4*>(F.table + o) = w[q][v];
+          if constexpr (OPT != HB_OPT_SGD) *reinterpret_cast<float4*>(F.slot0 + o) = s0[q][v];
+          if constexpr (OPT == HB_OPT_LAZY_ADAM) *reinterpret_cast<float4*>(F.slot1 + o) = s1[q][v];
         }
-      first = false;
+    } else {
+      sink_row<V, OPT, MODE, FAST>(P, F, M.key[q], M.us[q], acc[q], col, act, oob);
     }
-    __syncwarp();
-    // group sums -> piece sum, fixed order: g0 += g(ng/2) ... (groups beyond the
-    // piece hold zeros)
+  }
+}
+
+// bags (and gradient scales) of a piece: lane r holds rows r and r + 32
+__device__ __forceinline__ void piece_bags(const UpdParams& P, const LongItem& it, unsigned lane,
+                                           int (&bag)[2], float (&sc)[2]) {
+  const UpdFeat& F = P.f[it.feat];
+  const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
 #pragma unroll
-    for (int v = 0; v < V; ++v)
-      for (int off = ng >> 1; off >= 1; off >>= 1) {
-        float4 y;
-        y.x = __shfl_down_sync(0xffffffffu, acc[v].x, off << log2g);
-        y.y = __shfl_down_sync(0xffffffffu, acc[v].y, off << log2g);
-        y.z = __shfl_down_sync(0xffffffffu, acc[v].z, off << log2g);
-        y.w = __shfl_down_sync(0xffffffffu, acc[v].w, off << log2g);
-        if (gi < off) acc[v] = f4_add_rn(acc[v], y);
-      }
-    if (np == 1) {
-      if (gi == 0) sink_row<V, OPT, MODE, FAST>(P, F, key, item.u, acc, col, act, oob);
-      continue;
+  for (int r = 0; r < 2; ++r) {
+    const int j = r * 32 + (int)lane;
+    bag[r] = j < it.count ? entry_bag(F, it.start + j) : 0;
+    sc[r] = (scaled && j < it.count) ? bag_scale(F, bag[r]) : 1.0f;
+  }
+}
+
+template <int V, int OPT, int MODE, bool FAST>
+__global__ void __launch_bounds__(kUpdThreads, (V == 1 ? 3 : (V == 2 ? 2 : 1)))
+update_apply_kernel(const __grid_constant__ UpdParams P) {
+  extern __shared__ __align__(128) unsigned char s_dyn[];  // [warps][kStageBytes]
+  __shared__ int s_begin[kMaxUpdFeats + 1];
+  constexpr int kBatch = (V == 1) ? 8 : (V == 2 ? 4 : 2);  // partial rows in flight (final combine)
+  wait_spec(P.wait, P.status);
+  const unsigned lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  // dense map of the short work: warp units of (32 >> log2g) * kNU unique rows
+  int units = 0;
+  if ((int)threadIdx.x < P.nfeats) {
+    const int uc = (32 >> P.f[threadIdx.x].log2g) * kNU;
+    units = (P.f[threadIdx.x].counts[0] + uc - 1) / uc;
+    if (units > P.f[threadIdx.x].max_chunks) units = P.f[threadIdx.x].max_chunks;
+  }
+  const int n_short = seg_scan(P.nfeats, units, s_begin);
+  int n_long = P.long_count[0];
+  if (n_long > P.item_cap) n_long = P.item_cap;
+  // Work is handed out by two global tickets (pieces, short units; zeroed with the queue),
+  // two tickets ahead of use so that the descriptor of the next unit can be prefetched.
+  // Half of the warps of every CTA start on the pieces, the others on the short runs;
+  // a warp that runs out of its kind continues with the other one.
+  auto grab = [&](int which) -> int {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(&P.long_count[P.ticket_base + which], 1);
+    return __shfl_sync(0xffffffffu, v, 0);
+  };
+  bool oob = false;
+  const bool long_first = (warp & 1) != 0 && n_long > 0;
+  for (int round = 0; round < 2; ++round) {
+  const bool do_long = (round == 0) == long_first;
+  if (!do_long) {
+    // ---- short runs -----------------------------------------------------------------------
+    int unit = grab(1);
+    int next = grab(1);
+    ShortMeta M, Mn;
+    if (unit < n_short) short_meta(P, s_begin, unit, lane, M);
+    while (unit < n_short) {
+      const int next2 = grab(1);
+      // the NEXT unit's run bounds travel while this unit's rows do
+      if (next < n_short) short_meta(P, s_begin, next, lane, Mn);
+      short_unit<V, OPT, MODE, FAST>(P, M, lane, oob);
+      M = Mn;
+      unit = next;
+      next = next2;
     }
-    // multi-piece run: park the piece sum; the warp arriving last adds all pieces in
-    // piece order (which warp that is does not change the order of the additions)
-    float* prow = P.part + (size_t)(item.pbase + item.piece) * P.part_stride;
-    if (gi == 0) {
+  } else {
+    // ---- hot-row pieces: one warp per piece, rows staged with cp.async ------------------
+    float* stage = reinterpret_cast<float*>(s_dyn + (size_t)warp * kStageBytes);
+    int it = grab(0);
+    int itn = grab(0);
+    LongItem cur, nxt;
+    int bag[2], nbag[2];
+    float sc[2], nsc[2];
+    if (it < n_long) {
+      cur = P.items[it];
+      piece_bags(P, cur, lane, bag, sc);
+    }
+    while (it < n_long) {
+      const UpdFeat& F = P.f[cur.feat];
+      if (F.max_chunks == 0) {           // a feature of another vector class: not this launch's
+        it = itn;
+        itn = grab(0);
+        if (it < n_long) { cur = P.items[it]; piece_bags(P, cur, lane, bag, sc); }
+        continue;
+      }
+      const int log2g = F.log2g;
+      const int G = 1 << log2g;
+      const int ng = 32 >> log2g;        // groups per warp
+      const int gi = (int)lane >> log2g;
+      const int l = (int)lane & (G - 1);
+      const int dim = F.dim;
+      const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
+      int col[V];
+      bool act[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        col[v] = ((v << log2g) + l) * 4;
+        act[v] = col[v] < dim;
+      }
+      const int m = cur.count;
+      // (1) start the copies of all rows of the piece: group gi fetches rows gi, gi + ng, ...
+      for (int t0 = 0; t0 < m; t0 += ng) {   // warp-uniform trip count
+        const int j = t0 + gi;
+        const int b = __shfl_sync(0xffffffffu, bag[t0 >> 5], j & 31);
+        if (j < m) {
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            if (act[v]) cp_async16(stage + (size_t)j * dim + col[v], F.grad + (int64_t)b * F.grad_stride + col[v]);
+        }
+      }
+      // (2) the next piece's descriptor travels meanwhile
+      const int itn2 = grab(0);
+      if (itn < n_long) nxt = P.items[itn];
+      // (3) rows have landed
+      cp_async_wait_all();
+      __syncwarp();
+      // (4) the next piece's bags travel while this piece is added up
+      if (itn < n_long) piece_bags(P, nxt, lane, nbag, nsc);
+      // (5) group gi adds rows gi, gi + ng, ... in that order
+      float4 acc[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = f4_zero();
+      bool first = true;
+      for (int t0 = 0; t0 < m; t0 += ng) {
+        const int j = t0 + gi;
+        const float c = __shfl_sync(0xffffffffu, sc[t0 >> 5], j & 31);
+        if (j < m) {
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            if (act[v]) {
+              float4 t = *reinterpret_cast<const float4*>(stage + (size_t)j * dim + col[v]);
+              if (scaled) t = f4_div_rn(t, c);
+              acc[v] = first ? t : f4_add_rn(acc[v], t);
+            }
+          first = false;
+        }
+      }
+      __syncwarp();  // the stage may be overwritten by the next piece from here on
+      // group sums -> piece sum, fixed order: g0 += g(ng/2) ... (idle groups hold zeros)
 #pragma unroll
       for (int v = 0; v < V; ++v)
-        if (act[v]) *reinterpret_cast<float4*>(prow + col[v]) = acc[v];
-    }
-    __threadfence();
-    __syncwarp();
-    int old = 0;
-    if (lane == 0) old = atomicAdd(&P.tickets[item.pbase], 1);
-    old = __shfl_sync(0xffffffffu, old, 0);
-    if (old != np - 1) continue;  // warp-uniform
-    __threadfence();
-    // group gi adds pieces gi, gi + ng, ...; the group sums are combined as above
-    const float* p0 = P.part + (size_t)item.pbase * P.part_stride;
-    float4 tot[V];
+        for (int off = ng >> 1; off >= 1; off >>= 1) {
+          float4 y;
+          y.x = __shfl_down_sync(0xffffffffu, acc[v].x, off << log2g);
+          y.y = __shfl_down_sync(0xffffffffu, acc[v].y, off << log2g);
+          y.z = __shfl_down_sync(0xffffffffu, acc[v].z, off << log2g);
+          y.w = __shfl_down_sync(0xffffffffu, acc[v].w, off << log2g);
+          if (gi < off) acc[v] = f4_add_rn(acc[v], y);
+        }
+      bool last = false;
+      if (cur.np == 1) {
+        if (gi == 0) sink_row<V, OPT, MODE, FAST>(P, F, cur.key, cur.u, acc, col, act, oob);
+      } else {
+        // multi-piece run: park the piece sum; the warp arriving last adds all pieces in
+        // piece order (which warp that is does not change the order of the additions)
+        float* prow = P.part + (size_t)(cur.pbase + cur.piece) * P.part_stride;
+        if (gi == 0) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) tot[v] = f4_zero();
-    bool first2 = true;
-    for (int j0 = gi; j0 < np; j0 += ng * kBatch) {  // warp-uniform trip count
-      float4 x[kBatch][V];
+          for (int v = 0; v < V; ++v)
+            if (act[v]) *reinterpret_cast<float4*>(prow + col[v]) = acc[v];
+        }
+        __threadfence();
+        __syncwarp();
+        int old = 0;
+        if (lane == 0) old = atomicAdd(&P.tickets[cur.pbase], 1);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        last = (old == cur.np - 1);  // warp-uniform
+      }
+      if (last) {
+        __threadfence();
+        // group gi adds pieces gi, gi + ng, ...; the group sums are combined as above
+        const float* p0 = P.part + (size_t)cur.pbase * P.part_stride;
+        float4 tot[V];
 #pragma unroll
-      for (int i = 0; i < kBatch; ++i)
+        for (int v = 0; v < V; ++v) tot[v] = f4_zero();
+        bool first2 = true;
+        for (int j0 = gi; j0 - gi < cur.np; j0 += ng * kBatch) {  // warp-uniform trip count
+          float4 x[kBatch][V];
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i)
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+              x[i][v] = (j0 + i * ng < cur.np && act[v])
+                            ? ld_cg_f4(reinterpret_cast<const float4*>(p0 + (size_t)(j0 + i * ng) * P.part_stride + col[v]))
+                            : f4_zero();
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i)
+            if (j0 + i * ng < cur.np) {
+#pragma unroll
+              for (int v = 0; v < V; ++v) tot[v] = first2 ? x[i][v] : f4_add_rn(tot[v], x[i][v]);
+              first2 = false;
+            }
+        }
 #pragma unroll
         for (int v = 0; v < V; ++v)
-          x[i][v] = (j0 + i * ng < np && act[v])
-                        ? ld_cg_f4(reinterpret_cast<const float4*>(p0 + (size_t)(j0 + i * ng) * P.part_stride + col[v]))
-                        : f4_zero();
-#pragma unroll
-      for (int i = 0; i < kBatch; ++i)
-        if (j0 + i * ng < np) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) tot[v] = first2 ? x[i][v] : f4_add_rn(tot[v], x[i][v]);
-          first2 = false;
-        }
-    }
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-      for (int off = ng >> 1; off >= 1; off >>= 1) {
-        float4 y;
-        y.x = __shfl_down_sync(0xffffffffu, tot[v].x, off << log2g);
-        y.y = __shfl_down_sync(0xffffffffu, tot[v].y, off << log2g);
-        y.z = __shfl_down_sync(0xffffffffu, tot[v].z, off << log2g);
-        y.w = __shfl_down_sync(0xffffffffu, tot[v].w, off << log2g);
-        if (gi < off) tot[v] = f4_add_rn(tot[v], y);
+          for (int off = ng >> 1; off >= 1; off >>= 1) {
+            float4 y;
+            y.x = __shfl_down_sync(0xffffffffu, tot[v].x, off << log2g);
+            y.y = __shfl_down_sync(0xffffffffu, tot[v].y, off << log2g);
+            y.z = __shfl_down_sync(0xffffffffu, tot[v].z, off << log2g);
+            y.w = __shfl_down_sync(0xffffffffu, tot[v].w, off << log2g);
+            if (gi < off) tot[v] = f4_add_rn(tot[v], y);
+          }
+        if (gi == 0) sink_row<V, OPT, MODE, FAST>(P, F, cur.key, cur.u, tot, col, act, oob);
       }
-    if (gi == 0) sink_row<V, OPT, MODE, FAST>(P, F, key, item.u, tot, col, act, oob);
+      cur = nxt;
+      bag[0] = nbag[0]; bag[1] = nbag[1];
+      sc[0] = nsc[0]; sc[1] = nsc[1];
+      it = itn;
+      itn = itn2;
+    }
   }
+  }  // round
   if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
 }
 
@@ -765,9 +906,9 @@ static UpdLayout upd_layout(const hbUpdateFeature& f, size_t base) {
 
 // chunk-shared scratch behind the per-feature regions
 struct SharedLayout {
-  size_t zero_sort, zero_sort_bytes;    // bucket scratch + run status/ticket: zeroed per sort
+  // zeroed per sort: bucket scratch, run status/ticket, hot-row queue counters and tickets
+  size_t zero_sort, zero_sort_bytes;
   size_t bucket, run_status, run_ticket;
-  size_t zero_apply, zero_apply_bytes;  // long-run counters + tickets: zeroed per apply
   size_t long_count, tickets;
   size_t items, part;
   size_t end;
@@ -791,14 +932,12 @@ static SharedLayout shared_layout(size_t base, int nc, size_t total_tiles, size_
   S.bucket = take(bucket_scratch_words(nc, total_tiles, kRadixBins, kMaxPasses) * sizeof(uint32_t));
   S.run_status = take((run_tiles + (size_t)nc + 1) * sizeof(uint32_t));
   S.run_ticket = take(64);
-  S.zero_sort_bytes = o - S.zero_sort;
   S.item_cap = (int)item_cap;
   S.part_cap = (int)part_cap;
   S.part_stride = (max_dim + 3) / 4 * 4;
-  S.zero_apply = o;
   S.long_count = take(64);
   S.tickets = take((size_t)S.part_cap * sizeof(int32_t));
-  S.zero_apply_bytes = o - S.zero_apply;
+  S.zero_sort_bytes = o - S.zero_sort;
   S.items = take((size_t)S.item_cap * sizeof(LongItem));
   S.part = take((size_t)S.part_cap * S.part_stride * sizeof(float));
   S.end = o;
@@ -809,30 +948,17 @@ static inline size_t run_tiles_of(int64_t nnz) { return (size_t)((nnz + kRunTile
 
 template <int V, int OPT, int MODE, bool FAST>
 static int launch_apply(const UpdParams& U, int max_short_ctas, cudaStream_t stream) {
-  const int sms = device_sm_count();
-  {
-    int per_sm = 0;
-    HB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &per_sm, update_short_kernel<V, OPT, MODE, FAST>, kUpdThreads, 0));
-    int grid = sms * (per_sm > 0 ? per_sm : 1);
-    if (grid > max_short_ctas) grid = max_short_ctas;
-    if (grid < 1) grid = 1;
-    KernelScope ks(HB_K_SPARSE_UPDATE, stream);
-    update_short_kernel<V, OPT, MODE, FAST><<<grid, kUpdThreads, 0, stream>>>(U);
-    HB_CUDA_OK(cudaGetLastError());
-  }
-  {
-    const size_t smem = (size_t)kLongWarps * kStageBytes + (size_t)kLongWarps * kMaxPiece * sizeof(float);
-    HB_CUDA_OK(cudaFuncSetAttribute(update_long_kernel<V, OPT, MODE, FAST>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = sms;  // one CTA of kLongWarps stage buffers per SM
-    const int need = (U.item_cap + kLongWarps - 1) / kLongWarps;
-    if (grid > need) grid = need;
-    if (grid < 1) grid = 1;
-    KernelScope ks(HB_K_UPDATE_LONG, stream);
-    update_long_kernel<V, OPT, MODE, FAST><<<grid, kLongWarps * 32, smem, stream>>>(U);
-    HB_CUDA_OK(cudaGetLastError());
-  }
+  (void)max_short_ctas;
+  const size_t smem = (size_t)(kUpdThreads / 32) * kStageBytes;
+  HB_CUDA_OK(cudaFuncSetAttribute(update_apply_kernel<V, OPT, MODE, FAST>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  HB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+      &per_sm, update_apply_kernel<V, OPT, MODE, FAST>, kUpdThreads, smem));
+  const int grid = device_sm_count() * (per_sm > 0 ? per_sm : 1);
+  KernelScope ks(HB_K_SPARSE_UPDATE, stream);
+  update_apply_kernel<V, OPT, MODE, FAST><<<grid, kUpdThreads, smem, stream>>>(U);
+  HB_CUDA_OK(cudaGetLastError());
   return HB_OK;
 }
 
@@ -906,7 +1032,7 @@ static int radix_passes(int64_t space) {
 }
 
 size_t sparse_update_workspace_bytes(int n, const hbUpdateFeature* feats) {
-  size_t o = 0, max_shared = 0;
+  size_t o = 0, shared_total = 0;
   for (int c0 = 0; c0 < n; c0 += kMaxUpdFeats) {
     const int nc = (n - c0 < kMaxUpdFeats) ? n - c0 : kMaxUpdFeats;
     size_t tiles = 0, rtiles = 0, items = 64, parts = 64;
@@ -920,10 +1046,10 @@ size_t sparse_update_workspace_bytes(int n, const hbUpdateFeature* feats) {
       parts += long_parts_of(f.nnz, f.dim);
       if (f.dim > max_dim) max_dim = f.dim;
     }
-    const size_t sb = shared_layout(0, nc, tiles, rtiles, items, parts, max_dim).end;
-    if (sb > max_shared) max_shared = sb;
+    // one shared region per chunk: the hot-row queue lives from the sort phase to the apply
+    shared_total += align_up(shared_layout(0, nc, tiles, rtiles, items, parts, max_dim).end, 256);
   }
-  return align_up(o, 256) + max_shared + 256;
+  return align_up(o, 256) + shared_total + 256;
 }
 
 // Sort (row key, bag) pairs of every feature, find the runs and run the fused
@@ -954,6 +1080,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
   int rc = HB_OK;
 
   size_t off = 0;
+  size_t shared_off = align_up(feat_end, 256);
   for (int c0 = 0; c0 < n; c0 += kMaxUpdFeats) {
     const int nc = (n - c0 < kMaxUpdFeats) ? n - c0 : kMaxUpdFeats;
     UpdLayout L[kMaxUpdFeats];
@@ -983,7 +1110,8 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
       }
     }
     off = o;
-    const SharedLayout S = shared_layout(feat_end, nc, total_tiles, total_rtiles, total_items, total_parts, max_dim);
+    const SharedLayout S = shared_layout(shared_off, nc, total_tiles, total_rtiles, total_items, total_parts, max_dim);
+    shared_off = align_up(S.end, 256);
 
     if (phases & kPhaseSort) {
       // 1. bag map for CSR features
@@ -1109,9 +1237,34 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
       }
       const int maxg = device_sm_count() * 4;
       const int grid = static_tiles < (size_t)maxg ? (int)static_tiles : maxg;
-      KernelScope ks(HB_K_RUNS, stream);
-      runs_kernel<<<grid, kUpdThreads, 0, stream>>>(R);
-      HB_CUDA_OK(cudaGetLastError());
+      {
+        KernelScope ks(HB_K_RUNS, stream);
+        runs_kernel<<<grid, kUpdThreads, 0, stream>>>(R);
+        HB_CUDA_OK(cudaGetLastError());
+      }
+      // 4. queue of hot rows
+      QueueParams Q;
+      Q.long_count = reinterpret_cast<int32_t*>(base + S.long_count);
+      Q.items = reinterpret_cast<LongItem*>(base + S.items);
+      Q.status = d_status;
+      Q.item_cap = S.item_cap; Q.part_cap = S.part_cap;
+      Q.nfeats = nc;
+      int qctas = 0;
+      for (int k = 0; k < nc; ++k) {
+        const hbUpdateFeature& f = feats[c0 + k];
+        Q.f[k].ustart = reinterpret_cast<int32_t*>(base + L[k].ustart);
+        Q.f[k].ukey = reinterpret_cast<uint32_t*>(base + L[k].ukey);
+        Q.f[k].counts = reinterpret_cast<int32_t*>(base + L[k].counts);
+        Q.f[k].piece = piece_rows(f.dim);
+        Q.f[k].max_chunks = (int)((f.nnz + kUpdThreads - 1) / kUpdThreads);
+        qctas += Q.f[k].max_chunks;
+      }
+      if (qctas > 0) {
+        const int qgrid = qctas < maxg ? qctas : maxg;
+        KernelScope ks(HB_K_UPDATE_LONG, stream);
+        queue_kernel<<<qgrid, kUpdThreads, 0, stream>>>(Q);
+        HB_CUDA_OK(cudaGetLastError());
+      }
     }
 
     // 4./5. fused duplicate-sum + sink, one launch pair per V class
@@ -1127,6 +1280,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
       U.part = reinterpret_cast<float*>(base + S.part);
       U.tickets = reinterpret_cast<int32_t*>(base + S.tickets);
       U.item_cap = S.item_cap; U.part_cap = S.part_cap; U.part_stride = S.part_stride;
+      U.ticket_base = 2 + 2 * (V == 1 ? 0 : (V == 2 ? 1 : (V == 4 ? 2 : 3)));
       U.nfeats = 0;
       U.opt = opt->kind;
       U.fast = (opt->flags & HB_OPT_FLAG_FAST_MATH) ? 1 : 0;
@@ -1139,11 +1293,14 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
                        (1.0 - pow((double)opt->beta1, t)));
       }
       int max_ctas = 0;
+      bool any = false;
+      U.nfeats = nc;  // queued pieces name features by their index in the chunk
       for (int k = 0; k < nc; ++k) {
         const hbUpdateFeature& f = feats[c0 + k];
         const UpdExtra* ex = extras ? &extras[c0 + k] : nullptr;
-        if (L[k].V != V || f.nnz == 0) continue;
-        UpdFeat& F = U.f[U.nfeats];
+        const bool sel = L[k].V == V && f.nnz > 0;
+        any = any || sel;
+        UpdFeat& F = U.f[k];
         const bool inA = (passes[k] & 1) == 1;
         F.table = f.table; F.slot0 = f.slot0; F.slot1 = f.slot1;
         F.grad = f.grad; F.offsets = f.offsets;
@@ -1161,14 +1318,12 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         F.rows = f.rows; F.grad_stride = f.grad_stride;
         F.dim = f.dim; F.combiner = f.combiner;
         F.log2g = L[k].log2g;
-        const int uc = (kUpdThreads >> L[k].log2g) * kNU;
-        F.max_chunks = (int)((f.nnz + uc - 1) / uc);
+        const int uc = (32 >> L[k].log2g) * kNU;
+        F.max_chunks = sel ? (int)((f.nnz + uc - 1) / uc) : 0;  // 0: not this launch's vector class
         F.piece = piece_rows(f.dim);
         max_ctas += F.max_chunks;
-        U.nfeats++;
       }
-      if (U.nfeats == 0) continue;
-      HB_CUDA_OK(cudaMemsetAsync(base + S.zero_apply, 0, S.zero_apply_bytes, stream));
+      if (!any) continue;
       rc = launch_apply_v(V, is_emit, U, max_ctas, stream);
       if (rc != HB_OK) return rc;
       wait = nullptr;  // later launches are stream-ordered behind the first

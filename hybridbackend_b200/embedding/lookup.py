@@ -115,6 +115,10 @@ class GroupLookup:
     self._saved = None
     self._sharded = None
     self._dense = {}  # replicated tables: dense gradient buffers and row ids
+    # descriptor cache: building ~80 ctypes structs per step costs more host time than
+    # the kernels take on the device, so struct arrays are kept per set of buffers
+    self._cache = {}
+    self._ev_ready = None
     world = collective.world_size if collective is not None else 1
     self.sharded_idx = [k for k, t in enumerate(self.tables)
                         if world > 1 and isinstance(t, ShardedEmbeddingWeights) and t.sharded]
@@ -130,31 +134,49 @@ class GroupLookup:
           [max_nnz[k] for k in self.sharded_idx], capacity_factor)
 
   # -- forward ---------------------------------------------------------------
+  def _memo(self, kind, key, build):
+    c = self._cache.setdefault(kind, {})
+    v = c.get(key)
+    if v is None:
+      if len(c) >= 16:
+        c.clear()
+      v = build()
+      c[key] = v
+    return v
+
   def forward(self, ids, offsets=None, out=None, check=False, prepare_backward=True):
     """ids[k]: int64 [nnz_k]; offsets[k]: int64 [B+1] or None.  Returns
     out [B, sum(dim)] float32 (feature k occupies columns col_offsets[k]:+dim)."""
     offsets = list(offsets) if offsets is not None else [None] * self.n
-    nbags = [ids[k].numel() if offsets[k] is None else offsets[k].numel() - 1
-             for k in range(self.n)]
-    B = nbags[0]
-    if any(b != B for b in nbags):
-      raise ValueError('all features of a GroupLookup must have the same number of bags')
-    for k in range(self.n):
-      _check_inputs(_weight_of(self.tables[k]), ids[k], offsets[k], f'GroupLookup feature {k}')
+    B = ids[0].numel() if offsets[0] is None else offsets[0].numel() - 1
     if out is None:
       out = torch.empty(B, self.out_dim, dtype=torch.float32, device=self.device)
+    in_key = (tuple(t.data_ptr() for t in ids), tuple(t.numel() for t in ids),
+              tuple(t.data_ptr() if t is not None else 0 for t in offsets), B)
+
+    def validate():
+      nbags = [ids[k].numel() if offsets[k] is None else offsets[k].numel() - 1 for k in range(self.n)]
+      if any(b != B for b in nbags):
+        raise ValueError('all features of a GroupLookup must have the same number of bags')
+      for k in range(self.n):
+        _check_inputs(_weight_of(self.tables[k]), ids[k], offsets[k], f'GroupLookup feature {k}')
+      return True
+    self._memo('valid', in_key, validate)
     st = _util.status_word(self.device)
     L = _lib.lib()
     with torch.cuda.device(self.device):
       self._sort_done = None
       if self.local_idx and prepare_backward and self.overlap_backward_sort:
-        self._presort(ids, offsets, B, st)
+        self._presort(ids, offsets, B, st, in_key)
       if self.local_idx:
-        feats = (_lib.hbLookupFeature * len(self.local_idx))()
-        for j, k in enumerate(self.local_idx):
-          feats[j] = _feature_struct(_weight_of(self.tables[k]), ids[k], offsets[k], B,
-                                     out[:, self.col_offsets[k]:], out.stride(0),
-                                     self.combiners[k])
+        def build():
+          feats = (_lib.hbLookupFeature * len(self.local_idx))()
+          for j, k in enumerate(self.local_idx):
+            feats[j] = _feature_struct(_weight_of(self.tables[k]), ids[k], offsets[k], B,
+                                       out[:, self.col_offsets[k]:], out.stride(0),
+                                       self.combiners[k])
+          return feats
+        feats = self._memo('fwd', (in_key, out.data_ptr(), out.stride(0)), build)
         _lib.check(L.hbGroupLookupForward(len(self.local_idx), feats,
                                           _lib.C.c_void_p(st.data_ptr()), _util.stream_ptr()),
                    'GroupLookup.forward')
@@ -162,7 +184,7 @@ class GroupLookup:
         self._sharded.forward([ids[k] for k in self.sharded_idx],
                               [offsets[k] for k in self.sharded_idx], B, out,
                               [self.col_offsets[k] for k in self.sharded_idx], st)
-    self._saved = (list(ids), offsets, B)
+    self._saved = (list(ids), offsets, B, in_key)
     if check:
       _util.check_status(self.device)
     return out
@@ -177,48 +199,58 @@ class GroupLookup:
       self._sharded.close()
       self._sharded = None
 
-  def _update_feats(self, ids, offsets, B, grad=None, optimizer=None):
-    m = len(self.local_idx)
-    feats = (_lib.hbUpdateFeature * m)()
-    for j, k in enumerate(self.local_idx):
-      w = _weight_of(self.tables[k])
-      slots = self._slots(k, optimizer) if optimizer is not None else []
-      feats[j] = _lib.hbUpdateFeature(
-          w.data_ptr(), slots[0].data_ptr() if len(slots) > 0 else None,
-          slots[1].data_ptr() if len(slots) > 1 else None, w.shape[0], ids[k].data_ptr(),
-          offsets[k].data_ptr() if offsets[k] is not None else None, B, ids[k].numel(),
-          grad[:, self.col_offsets[k]:].data_ptr() if grad is not None else None,
-          grad.stride(0) if grad is not None else w.shape[1], w.shape[1],
-          _lib.COMBINER[self.combiners[k]], 1)
-    return feats
+  def _update_feats(self, ids, offsets, B, grad=None, optimizer=None, in_key=None):
+    def build():
+      m = len(self.local_idx)
+      feats = (_lib.hbUpdateFeature * m)()
+      for j, k in enumerate(self.local_idx):
+        w = _weight_of(self.tables[k])
+        slots = self._slots(k, optimizer) if optimizer is not None else []
+        feats[j] = _lib.hbUpdateFeature(
+            w.data_ptr(), slots[0].data_ptr() if len(slots) > 0 else None,
+            slots[1].data_ptr() if len(slots) > 1 else None, w.shape[0], ids[k].data_ptr(),
+            offsets[k].data_ptr() if offsets[k] is not None else None, B, ids[k].numel(),
+            grad[:, self.col_offsets[k]:].data_ptr() if grad is not None else None,
+            grad.stride(0) if grad is not None else w.shape[1], w.shape[1],
+            _lib.COMBINER[self.combiners[k]], 1)
+      return feats, self._workspace_bytes(feats)
+    if in_key is None:
+      return build()
+    key = (in_key, grad.data_ptr() if grad is not None else 0, grad.stride(0) if grad is not None else 0,
+           optimizer.kind if optimizer is not None else '')
+    return self._memo('upd', key, build)
 
-  def _workspace(self, feats):
+  def _workspace_bytes(self, feats):
     need = _lib.C.c_size_t(0)
     _lib.check(_lib.lib().hbGroupSparseUpdateWorkspaceBytes(len(feats), feats, _lib.C.byref(need)),
                'GroupLookup workspace')
-    if self._upd_ws is None or self._upd_ws.numel() < need.value:
-      self._upd_ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=self.device)
+    return need.value
+
+  def _workspace(self, feats, need=None):
+    if need is None:
+      need = self._workspace_bytes(feats)
+    if self._upd_ws is None or self._upd_ws.numel() < need:
+      self._upd_ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
     return self._upd_ws
 
-  def _presort(self, ids, offsets, B, st):
-    """Enqueue the backward's id sort on the side stream (hbGroupSparseSort)."""
+  def _presort(self, ids, offsets, B, st, in_key=None):
+    """Enqueue the backward's id sort on the side stream (hbGroupSparseSort).  The ids
+    stay referenced by self._saved until the next forward, and the backward waits for
+    the side stream, so no allocator hand-over (record_stream) is needed."""
     if self._side is None:
       self._side = torch.cuda.Stream(device=self.device)
+      self._ev_ready = torch.cuda.Event()
+      self._ev_sorted = torch.cuda.Event()
     main = torch.cuda.current_stream()
-    feats = self._update_feats(ids, offsets, B)
-    ws = self._workspace(feats)
-    ready = torch.cuda.Event()
-    ready.record(main)
-    self._side.wait_event(ready)
-    for k in self.local_idx:
-      ids[k].record_stream(self._side)
-      if offsets[k] is not None:
-        offsets[k].record_stream(self._side)
+    feats, need = self._update_feats(ids, offsets, B, in_key=in_key)
+    ws = self._workspace(feats, need)
+    self._ev_ready.record(main)
+    self._side.wait_event(self._ev_ready)
     _lib.check(_lib.lib().hbGroupSparseSort(
         len(feats), feats, _lib.C.c_void_p(ws.data_ptr()), _lib.C.c_size_t(ws.numel()),
         _lib.C.c_void_p(st.data_ptr()), _lib.C.c_void_p(self._side.cuda_stream)), 'GroupLookup presort')
-    self._sort_done = torch.cuda.Event()
-    self._sort_done.record(self._side)
+    self._ev_sorted.record(self._side)
+    self._sort_done = self._ev_sorted
 
   def forward_host(self, h_ids, d_stage, out, h_out, check=False):
     """Host-buffer forward (one id per bag): h_ids pinned int64 [n, B] is copied
@@ -252,7 +284,7 @@ class GroupLookup:
             _lib.C.c_size_t(h_ids.numel() * 8), _lib.C.c_void_p(out.data_ptr()),
             _lib.C.c_void_p(h_out.data_ptr()), _lib.C.c_size_t(out.numel() * 4),
             _lib.C.c_void_p(st.data_ptr()), _util.stream_ptr()), 'GroupLookup.forward_host')
-        self._saved = (ids, [None] * self.n, B)
+        self._saved = (ids, [None] * self.n, B, None)
       else:
         d_stage.copy_(h_ids, non_blocking=True)
         self.forward(ids, out=out)
@@ -267,7 +299,7 @@ class GroupLookup:
     `optimizer` to every table in place (slots are created on first use)."""
     if self._saved is None:
       raise RuntimeError('GroupLookup.backward_update called before forward')
-    ids, offsets, B = self._saved
+    ids, offsets, B, in_key = self._saved
     _util.require_cuda(grad, 'GroupLookup.backward_update: grad')
     if grad.dtype != torch.float32 or grad.dim() != 2 or grad.shape[0] != B or \
         grad.shape[1] != self.out_dim or grad.stride(1) != 1:
@@ -280,9 +312,9 @@ class GroupLookup:
       if self.local_idx and self._sync():
         self._replicated_dense_update(ids, offsets, B, grad, optimizer, desc, st)
       elif self.local_idx:
-        feats = self._update_feats(ids, offsets, B, grad, optimizer)
+        feats, need = self._update_feats(ids, offsets, B, grad, optimizer, in_key=in_key)
         m = len(feats)
-        ws = self._workspace(feats)
+        ws = self._workspace(feats, need)
         if self._sort_done is not None:
           torch.cuda.current_stream().wait_event(self._sort_done)
           self._sort_done = None
