@@ -374,10 +374,14 @@ lookup_rows_tma_kernel(const __grid_constant__ LtParams P) {
   if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
 }
 
+// Opt-in (HB_TMA_GATHER=1).  Measured on B200 (profiles/r2_fwd_sweep.md): the copy-engine
+// gather loses to the register path at every row width of the target range -- 152 vs 79 us
+// (D=32), 193 vs 134 us (D=64), 291 vs 256 us (D=128) for 1.7 M rows -- because one bulk
+// copy per 128..512-byte row is bound by the per-SM bulk-copy issue rate, not by bytes.
 static bool use_tma_gather() {
   static const bool on = [] {
-    const char* e = getenv("HB_NO_TMA");
-    return !(e != nullptr && e[0] == '1');
+    const char* e = getenv("HB_TMA_GATHER");
+    return e != nullptr && e[0] == '1';
   }();
   return on;
 }

@@ -25,6 +25,7 @@
 // Algorithmic HBM bytes (Adagrad, fp32): per looked-up id 8 (sorted key + bag) +
 // 4*dim (gradient row); per unique row 4*4*dim (table + accumulator, read + write).
 #include <math.h>
+#include <stdlib.h>
 
 #include "bucket.cuh"
 #include "tma.cuh"
@@ -35,7 +36,6 @@ namespace hb {
 constexpr int kUpdThreads = 256;
 constexpr int kMaxUpdFeats = 96;
 constexpr int kShortMax = 16;   // runs up to this many entries are summed by one group
-constexpr int kNU = 2;          // unique rows in flight per group (short kernel)
 
 enum { kModeApply = 0, kModeEmit = 1 };
 
@@ -48,7 +48,7 @@ struct UpdFeat {
   const uint32_t* ukey;     // [U] unique keys
   const int32_t* ustart;    // [U+1]
   const int32_t* counts;    // [0] = U
-  const int32_t* uval;      // [U] value of the first entry of each run
+  const int4* ubag4;        // [U] values (bag / position) of the first four entries of each run
   const int32_t* vals;      // bag index of each sorted entry (or its position, see pos2bag)
   const int32_t* pos2bag;   // != nullptr: vals hold input positions, bag = pos2bag[position]
   const int32_t* emit_send_off;
@@ -82,7 +82,6 @@ struct UpdParams {
   float* part;              // [part_cap][part_stride] piece sums of multi-piece runs
   int32_t* tickets;         // [part_cap] arrival counters, indexed by the run's pbase
   int32_t item_cap, part_cap, part_stride;
-  int32_t ticket_base;      // work tickets of this launch: long_count[ticket_base + {0: pieces, 1: short units}]
   int32_t nfeats;
   int32_t opt;
   int32_t fast;             // approximate sqrt/div (MUFU) instead of the IEEE sequence
@@ -257,7 +256,7 @@ struct RunFeat {
   const int32_t* vals;
   uint32_t* ukey;
   int32_t* ustart;
-  int32_t* uval;          // value (bag / position) of the first entry of every run
+  int4* ubag4;            // values (bag / position) of the first four entries of every run
   int32_t* counts;        // [0] = U, [1] = valid entries
   int32_t* inv;           // may be nullptr
   int32_t* owner_start1;  // may be nullptr
@@ -355,7 +354,14 @@ __global__ void __launch_bounds__(kUpdThreads) runs_kernel(const __grid_constant
       if ((heads >> j) & 1u) {
         F.ukey[u] = k[j + 1];
         F.ustart[u] = i;
-        F.uval[u] = F.vals[i];
+        {  // first four values of the run (entries past its end are never used)
+          int4 b4;
+          b4.x = F.vals[i];
+          b4.y = (i + 1 < n) ? F.vals[i + 1] : 0;
+          b4.z = (i + 2 < n) ? F.vals[i + 2] : 0;
+          b4.w = (i + 3 < n) ? F.vals[i + 3] : 0;
+          F.ubag4[u] = b4;
+        }
         if (F.owner_start1 != nullptr) {
           const uint32_t own = k[j + 1] >> F.lbits;
           if (i == 0 || (k[j] >> F.lbits) != own) F.owner_start1[own] = u + 1;
@@ -378,9 +384,18 @@ __global__ void __launch_bounds__(kUpdThreads) runs_kernel(const __grid_constant
   if (oob) raise_status(P.d_status, HB_STATUS_ID_OUT_OF_RANGE);
 }
 
-// ---- 4. queue of hot rows ---------------------------------------------------------------
-// Runs longer than kShortMax are cut into pieces of `piece` entries and queued; the
-// apply kernel gives every piece to one warp.  Part of the sort phase (needs ids only).
+// ---- 4. apply ---------------------------------------------------------------------------
+// Two small kernels instead of one large one (the fused kernel of the previous design
+// spent a third of its issue slots waiting for instructions: 64 KB of code, two
+// divergent paths per CTA, 24 warps per SM):
+//   short kernel : one UNIQUE row per sub-warp group, static round-robin over the dense
+//                  unit list.  Run bounds, key and the first four bags of the run come
+//                  from the run arrays (prefetched one unit ahead), so a run of up to 4
+//                  entries costs ONE exposed memory round trip: table row, slot rows and
+//                  gradient rows are requested together.  Runs longer than kShortMax are
+//                  cut into pieces and queued (their groups do the queueing instead of
+//                  idling).
+//   long kernel  : one warp per queued piece, rows staged in shared memory with cp.async.
 constexpr int kStageBytes = 8192;              // bytes of gradient rows a warp stages per piece
 constexpr int kMaxPiece = 64;                  // rows per piece at most (two bag registers per lane)
 
@@ -391,81 +406,6 @@ static inline int piece_rows(int dim) {
   return p;
 }
 
-struct QueueFeat {
-  const int32_t* ustart;
-  const uint32_t* ukey;
-  const int32_t* counts;
-  int32_t piece;
-  int32_t max_chunks;
-};
-struct QueueParams {
-  QueueFeat f[kMaxUpdFeats];
-  int32_t* long_count;   // [0] queued pieces, [1] reserved partial slots
-  LongItem* items;
-  int32_t* status;
-  int32_t item_cap, part_cap;
-  int32_t nfeats;
-};
-
-__global__ void __launch_bounds__(kUpdThreads) queue_kernel(const __grid_constant__ QueueParams P) {
-  __shared__ int s_begin[kMaxUpdFeats + 1];
-  int units = 0;
-  if ((int)threadIdx.x < P.nfeats) {
-    units = (P.f[threadIdx.x].counts[0] + kUpdThreads - 1) / kUpdThreads;
-    if (units > P.f[threadIdx.x].max_chunks) units = P.f[threadIdx.x].max_chunks;
-  }
-  const int total = seg_scan(P.nfeats, units, s_begin);
-  const unsigned lane = lane_id();
-  for (int chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
-    const int fi = seg_find(s_begin, P.nfeats, chunk);
-    const QueueFeat& F = P.f[fi];
-    const int u = (chunk - s_begin[fi]) * kUpdThreads + (int)threadIdx.x;
-    int s = 0, len = 0;
-    if (u < F.counts[0]) {
-      s = F.ustart[u];
-      len = F.ustart[u + 1] - s;
-    }
-    const bool is_long = len > kShortMax;
-    const int np = is_long ? (len + F.piece - 1) / F.piece : 0;
-    int base = 0, pb = -1;
-    uint32_t key = 0;
-    if (is_long) {
-      base = atomicAdd(&P.long_count[0], np);
-      if (np > 1) pb = atomicAdd(&P.long_count[1], np);
-      key = F.ukey[u];
-      if (base + np > P.item_cap || (np > 1 && pb + np > P.part_cap)) {  // cannot happen by the layout bounds
-        raise_status(P.status, HB_STATUS_WINDOW_OVERFLOW);
-        base = -1;
-      }
-    }
-    // the pieces of a hot row are written by the whole warp (the hottest row of a
-    // power-law feature has hundreds of them)
-    unsigned todo = __ballot_sync(0xffffffffu, is_long && base >= 0);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int r_u = __shfl_sync(0xffffffffu, u, src);
-      const int r_s = __shfl_sync(0xffffffffu, s, src);
-      const int r_len = __shfl_sync(0xffffffffu, len, src);
-      const int r_np = __shfl_sync(0xffffffffu, np, src);
-      const int r_base = __shfl_sync(0xffffffffu, base, src);
-      const int r_pb = __shfl_sync(0xffffffffu, pb, src);
-      const uint32_t r_key = __shfl_sync(0xffffffffu, key, src);
-      for (int j = (int)lane; j < r_np; j += 32) {
-        LongItem it;
-        it.feat = fi; it.u = r_u; it.start = r_s + j * F.piece;
-        it.count = min(F.piece, r_len - j * F.piece);
-        it.key = r_key; it.pbase = r_pb; it.piece = j; it.np = r_np;
-        P.items[r_base + j] = it;
-      }
-    }
-  }
-}
-
-// ---- 5. apply: short runs and hot-row pieces in ONE launch ---------------------------------
-// Both kinds of work are chains of dependent memory round trips, so neither fills the
-// machine alone; warps of either kind share every SM.  The split of the warps between
-// the kinds is derived on the device from the amount of queued work.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
                :: "r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -474,154 +414,181 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-// run bounds, key and first value of the kNU unique rows a group owns in warp unit `unit`
+// run bounds, key and first bags of the unique row a group owns in warp unit `unit`
 struct ShortMeta {
-  int fi;
-  int us[kNU], s[kNU], len[kNU], v0[kNU];
-  uint32_t key[kNU];
+  int fi, u, s, len;
+  uint32_t key;
+  int4 b;
 };
 
 __device__ __forceinline__ void short_meta(const UpdParams& P, const int* s_begin, int unit, unsigned lane,
-                                           ShortMeta& M) {
-  M.fi = seg_find(s_begin, P.nfeats, unit);
-  const UpdFeat& F = P.f[M.fi];
+                                           int& fi_hint, ShortMeta& M) {
+  // units of one warp ascend: advance the feature instead of searching for it
+  int fi = fi_hint;
+  while (unit >= s_begin[fi + 1]) ++fi;
+  fi_hint = fi;
+  M.fi = fi;
+  const UpdFeat& F = P.f[fi];
   const int ng = 32 >> F.log2g;
   const int gi = (int)lane >> F.log2g;
   const int U = F.counts[0];
-  const int u0 = (unit - s_begin[M.fi]) * ng * kNU;
-#pragma unroll
-  for (int q = 0; q < kNU; ++q) {  // consecutive groups <-> consecutive uniques
-    M.us[q] = u0 + q * ng + gi;
-    const bool ok = M.us[q] < U;
-    const int uu = ok ? M.us[q] : 0;
-    M.s[q] = F.ustart[uu];
-    M.len[q] = ok ? F.ustart[uu + 1] - M.s[q] : 0;
-    M.key[q] = F.ukey[uu];
-    M.v0[q] = F.uval[uu];
-  }
+  M.u = (unit - s_begin[fi]) * ng + gi;
+  const bool ok = M.u < U;
+  const int uu = ok ? M.u : 0;
+  M.s = F.ustart[uu];
+  M.len = ok ? F.ustart[uu + 1] - M.s : 0;
+  M.key = F.ukey[uu];
+  M.b = F.ubag4[uu];
 }
 
-template <int V, int OPT, int MODE, bool FAST>
-__device__ __forceinline__ void short_unit(const UpdParams& P, ShortMeta& M, unsigned lane, bool& oob) {
-  const UpdFeat& F = P.f[M.fi];
-  const int log2g = F.log2g;
-  const int l = (int)lane & ((1 << log2g) - 1);
-  const int dim = F.dim;
-  const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
-  int col[V];
-  bool act[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    col[v] = ((v << log2g) + l) * 4;
-    act[v] = col[v] < dim;
+template <int V, int OPT, int MODE, bool FAST, int OCC>
+__global__ void __launch_bounds__(kUpdThreads, OCC)
+update_short_kernel(const __grid_constant__ UpdParams P) {
+  __shared__ int s_begin[kMaxUpdFeats + 2];
+  constexpr int NG = (V == 1) ? 4 : (V == 2 ? 2 : 1);   // gradient rows in flight per group
+  wait_spec(P.wait, P.status);
+  const unsigned lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  int units = 0;
+  if ((int)threadIdx.x < P.nfeats) {
+    const int ng = 32 >> P.f[threadIdx.x].log2g;
+    units = (P.f[threadIdx.x].counts[0] + ng - 1) / ng;
+    if (units > P.f[threadIdx.x].max_chunks) units = P.f[threadIdx.x].max_chunks;
   }
-  bool ok[kNU];
-#pragma unroll
-  for (int q = 0; q < kNU; ++q) {
-    ok[q] = M.len[q] > 0 && M.len[q] <= kShortMax;  // longer runs are queued pieces
-    if (MODE == kModeApply && ok[q] && (uint64_t)M.key[q] >= (uint64_t)F.rows) {
+  const int total = seg_scan(P.nfeats, units, s_begin);
+  if (threadIdx.x == 0) s_begin[P.nfeats + 1] = 0x7FFFFFFF;  // sentinel for the feature walk
+  __syncthreads();
+  const int nwarps = gridDim.x * (kUpdThreads / 32);
+  int unit = blockIdx.x * (kUpdThreads / 32) + warp;
+  bool oob = false;
+  int fi_hint = 0;
+  ShortMeta M, Mn;
+  if (unit < total) short_meta(P, s_begin, unit, lane, fi_hint, M);
+  while (unit < total) {
+    const int next = unit + nwarps;
+    // the NEXT unit's run bounds travel while this unit's rows do
+    if (next < total) short_meta(P, s_begin, next, lane, fi_hint, Mn);
+    const UpdFeat& F = P.f[M.fi];
+    const int log2g = F.log2g;
+    const int l = (int)lane & ((1 << log2g) - 1);
+    const int dim = F.dim;
+    // ---- hot rows: cut into pieces and queue them for the long kernel --------------------
+    {
+      const bool is_long = M.len > kShortMax && l == 0;
+      unsigned todo = __ballot_sync(0xffffffffu, is_long);
+      if (todo) {
+        const int np = is_long ? (M.len + F.piece - 1) / F.piece : 0;
+        int base = -1, pb = -1;
+        if (is_long) {
+          base = atomicAdd(&P.long_count[0], np);
+          if (np > 1) pb = atomicAdd(&P.long_count[1], np);
+          if (base + np > P.item_cap || (np > 1 && pb + np > P.part_cap)) {  // cannot happen by the layout bounds
+            raise_status(P.status, HB_STATUS_WINDOW_OVERFLOW);
+            base = -1;
+          }
+        }
+        todo = __ballot_sync(0xffffffffu, is_long && base >= 0);
+        while (todo) {  // the pieces of a hot row are written by the whole warp
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int r_u = __shfl_sync(0xffffffffu, M.u, src);
+          const int r_s = __shfl_sync(0xffffffffu, M.s, src);
+          const int r_len = __shfl_sync(0xffffffffu, M.len, src);
+          const int r_np = __shfl_sync(0xffffffffu, np, src);
+          const int r_base = __shfl_sync(0xffffffffu, base, src);
+          const int r_pb = __shfl_sync(0xffffffffu, pb, src);
+          const uint32_t r_key = __shfl_sync(0xffffffffu, M.key, src);
+          for (int j = (int)lane; j < r_np; j += 32) {
+            LongItem it;
+            it.feat = M.fi; it.u = r_u; it.start = r_s + j * F.piece;
+            it.count = min(F.piece, r_len - j * F.piece);
+            it.key = r_key; it.pbase = r_pb; it.piece = j; it.np = r_np;
+            P.items[r_base + j] = it;
+          }
+        }
+      }
+    }
+    // ---- short run: sum in position order, one read-modify-write -------------------------
+    bool ok = M.len > 0 && M.len <= kShortMax;
+    if (MODE == kModeApply && ok && (uint64_t)M.key >= (uint64_t)F.rows) {
       oob = true;
-      ok[q] = false;
+      ok = false;
     }
-    if (!ok[q]) M.len[q] = 0;
-  }
-  // one round trip: table row, slot rows, the gradient row of the run's first entry (its
-  // bag came with the run bounds) and the bags of entries 1..3
-  float4 w[kNU][V], s0[kNU][V], s1[kNU][V], acc[kNU][V];
-  float sc0[kNU];
-  int b1[kNU][3];
+    if (ok) {
+      const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
+      int col[V];
+      bool act[V];
 #pragma unroll
-  for (int q = 0; q < kNU; ++q) {
-    int bag0 = M.v0[q];
-    if (ok[q] && F.pos2bag != nullptr) bag0 = F.pos2bag[bag0];
-    sc0[q] = (scaled && ok[q]) ? bag_scale(F, bag0) : 1.0f;
+      for (int v = 0; v < V; ++v) {
+        col[v] = ((v << log2g) + l) * 4;
+        act[v] = col[v] < dim;
+      }
+      float4 w[V], s0[V], s1[V], acc[V];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) b1[q][i] = (1 + i < M.len[q]) ? entry_bag(F, M.s[q] + 1 + i) : -1;
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      w[q][v] = s0[q][v] = s1[q][v] = acc[q][v] = f4_zero();
-      if (ok[q] && act[v]) {
-        acc[q][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.grad + (int64_t)bag0 * F.grad_stride + col[v]));
+      for (int v = 0; v < V; ++v) {
+        w[v] = s0[v] = s1[v] = acc[v] = f4_zero();
         if constexpr (MODE == kModeApply) {
-          const int64_t o = (int64_t)M.key[q] * dim + col[v];
-          w[q][v] = *reinterpret_cast<const float4*>(F.table + o);
-          if constexpr (OPT != HB_OPT_SGD) s0[q][v] = *reinterpret_cast<const float4*>(F.slot0 + o);
-          if constexpr (OPT == HB_OPT_LAZY_ADAM) s1[q][v] = *reinterpret_cast<const float4*>(F.slot1 + o);
+          if (act[v]) {
+            const int64_t o = (int64_t)M.key * dim + col[v];
+            w[v] = *reinterpret_cast<const float4*>(F.table + o);
+            if constexpr (OPT != HB_OPT_SGD) s0[v] = *reinterpret_cast<const float4*>(F.slot0 + o);
+            if constexpr (OPT == HB_OPT_LAZY_ADAM) s1[v] = *reinterpret_cast<const float4*>(F.slot1 + o);
+          }
         }
       }
-    }
-  }
+      for (int j0 = 0; j0 < M.len; j0 += NG) {
+        int bag[NG];
+        float sc[NG];
+        float4 x[NG][V];
 #pragma unroll
-  for (int q = 0; q < kNU; ++q) {
-    if (scaled) {
-#pragma unroll
-      for (int v = 0; v < V; ++v) acc[q][v] = f4_div_rn(acc[q][v], sc0[q]);
-    }
-    if (M.len[q] > 1) {
-      // entries 1..3 (bags already here), then 4.. in fours; added in position order
-      float4 x[3][V];
-      float c3[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        c3[i] = (scaled && b1[q][i] >= 0) ? bag_scale(F, b1[q][i]) : 1.0f;
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          x[i][v] = f4_zero();
-          if (b1[q][i] >= 0 && act[v])
-            x[i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
-                F.grad + (int64_t)b1[q][i] * F.grad_stride + col[v]));
+        for (int i = 0; i < NG; ++i) {
+          const int j = j0 + i;
+          int vv = -1;
+          if (j < M.len) {
+            if (j < 4) vv = (j == 0) ? M.b.x : (j == 1 ? M.b.y : (j == 2 ? M.b.z : M.b.w));
+            else vv = F.vals[M.s + j];
+            if (F.pos2bag != nullptr) vv = F.pos2bag[vv];
+          }
+          bag[i] = vv;
         }
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+          sc[i] = (scaled && bag[i] >= 0) ? bag_scale(F, bag[i]) : 1.0f;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            x[i][v] = f4_zero();
+            if (bag[i] >= 0 && act[v])
+              x[i][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.grad + (int64_t)bag[i] * F.grad_stride + col[v]));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NG; ++i)
+          if (bag[i] >= 0) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float4 t = scaled ? f4_div_rn(x[i][v], sc[i]) : x[i][v];
+              acc[v] = (j0 + i == 0) ? t : f4_add_rn(acc[v], t);
+            }
+          }
       }
+      if constexpr (MODE == kModeApply) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
-        if (b1[q][i] >= 0)
-#pragma unroll
-          for (int v = 0; v < V; ++v)
-            acc[q][v] = f4_add_rn(acc[q][v], scaled ? f4_div_rn(x[i][v], c3[i]) : x[i][v]);
-    }
-    for (int j0 = 4; j0 < M.len[q]; j0 += 4) {
-      int b4[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) b4[i] = (j0 + i < M.len[q]) ? entry_bag(F, M.s[q] + j0 + i) : -1;
-      float4 x[4][V];
-      float c4[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        c4[i] = (scaled && b4[i] >= 0) ? bag_scale(F, b4[i]) : 1.0f;
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          x[i][v] = f4_zero();
-          if (b4[i] >= 0 && act[v])
-            x[i][v] = ld_nc_f4(reinterpret_cast<const float4*>(
-                F.grad + (int64_t)b4[i] * F.grad_stride + col[v]));
-        }
+        for (int v = 0; v < V; ++v)
+          if (act[v]) {
+            const int64_t o = (int64_t)M.key * dim + col[v];
+            opt_step4<OPT, FAST>(P, w[v], s0[v], s1[v], acc[v]);
+            *reinterpret_cast<float4*>(F.table + o) = w[v];
+            if constexpr (OPT != HB_OPT_SGD) *reinterpret_cast<float4*>(F.slot0 + o) = s0[v];
+            if constexpr (OPT == HB_OPT_LAZY_ADAM) *reinterpret_cast<float4*>(F.slot1 + o) = s1[v];
+          }
+      } else {
+        sink_row<V, OPT, MODE, FAST>(P, F, M.key, M.u, acc, col, act, oob);
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (b4[i] >= 0)
-#pragma unroll
-          for (int v = 0; v < V; ++v)
-            acc[q][v] = f4_add_rn(acc[q][v], scaled ? f4_div_rn(x[i][v], c4[i]) : x[i][v]);
     }
+    M = Mn;
+    unit = next;
   }
-  // sink
-#pragma unroll
-  for (int q = 0; q < kNU; ++q) {
-    if (!ok[q]) continue;
-    if constexpr (MODE == kModeApply) {
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (act[v]) {
-          const int64_t o = (int64_t)M.key[q] * dim + col[v];
-          opt_step4<OPT, FAST>(P, w[q][v], s0[q][v], s1[q][v], acc[q][v]);
-          *reinterpret_cast<float4*>(F.table + o) = w[q][v];
-          if constexpr (OPT != HB_OPT_SGD) *reinterpret_cast<float4*>(F.slot0 + o) = s0[q][v];
-          if constexpr (OPT == HB_OPT_LAZY_ADAM) *reinterpret_cast<float4*>(F.slot1 + o) = s1[q][v];
-        }
-    } else {
-      sink_row<V, OPT, MODE, FAST>(P, F, M.key[q], M.us[q], acc[q], col, act, oob);
-    }
-  }
+  if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
 }
 
 // bags (and gradient scales) of a piece: lane r holds rows r and r + 32
@@ -637,201 +604,159 @@ __device__ __forceinline__ void piece_bags(const UpdParams& P, const LongItem& i
   }
 }
 
+// Hot rows: one warp per queued piece (static round-robin), rows staged with cp.async.
 template <int V, int OPT, int MODE, bool FAST>
 __global__ void __launch_bounds__(kUpdThreads, (V == 1 ? 3 : (V == 2 ? 2 : 1)))
-update_apply_kernel(const __grid_constant__ UpdParams P) {
+update_long_kernel(const __grid_constant__ UpdParams P) {
   extern __shared__ __align__(128) unsigned char s_dyn[];  // [warps][kStageBytes]
-  __shared__ int s_begin[kMaxUpdFeats + 1];
   constexpr int kBatch = (V == 1) ? 8 : (V == 2 ? 4 : 2);  // partial rows in flight (final combine)
-  wait_spec(P.wait, P.status);
   const unsigned lane = lane_id();
   const int warp = threadIdx.x >> 5;
-  // dense map of the short work: warp units of (32 >> log2g) * kNU unique rows
-  int units = 0;
-  if ((int)threadIdx.x < P.nfeats) {
-    const int uc = (32 >> P.f[threadIdx.x].log2g) * kNU;
-    units = (P.f[threadIdx.x].counts[0] + uc - 1) / uc;
-    if (units > P.f[threadIdx.x].max_chunks) units = P.f[threadIdx.x].max_chunks;
-  }
-  const int n_short = seg_scan(P.nfeats, units, s_begin);
   int n_long = P.long_count[0];
   if (n_long > P.item_cap) n_long = P.item_cap;
-  // Work is handed out by two global tickets (pieces, short units; zeroed with the queue),
-  // two tickets ahead of use so that the descriptor of the next unit can be prefetched.
-  // Half of the warps of every CTA start on the pieces, the others on the short runs;
-  // a warp that runs out of its kind continues with the other one.
-  auto grab = [&](int which) -> int {
-    int v = 0;
-    if (lane == 0) v = atomicAdd(&P.long_count[P.ticket_base + which], 1);
-    return __shfl_sync(0xffffffffu, v, 0);
-  };
+  const int nwarps = gridDim.x * (kUpdThreads / 32);
   bool oob = false;
-  const bool long_first = (warp & 1) != 0 && n_long > 0;
-  for (int round = 0; round < 2; ++round) {
-  const bool do_long = (round == 0) == long_first;
-  if (!do_long) {
-    // ---- short runs -----------------------------------------------------------------------
-    int unit = grab(1);
-    int next = grab(1);
-    ShortMeta M, Mn;
-    if (unit < n_short) short_meta(P, s_begin, unit, lane, M);
-    while (unit < n_short) {
-      const int next2 = grab(1);
-      // the NEXT unit's run bounds travel while this unit's rows do
-      if (next < n_short) short_meta(P, s_begin, next, lane, Mn);
-      short_unit<V, OPT, MODE, FAST>(P, M, lane, oob);
-      M = Mn;
-      unit = next;
-      next = next2;
+  float* stage = reinterpret_cast<float*>(s_dyn + (size_t)warp * kStageBytes);
+  int it = blockIdx.x * (kUpdThreads / 32) + warp;
+  LongItem cur, nxt;
+  int bag[2], nbag[2];
+  float sc[2], nsc[2];
+  if (it < n_long) {
+    cur = P.items[it];
+    piece_bags(P, cur, lane, bag, sc);
+  }
+  while (it < n_long) {
+    const int itn = it + nwarps;
+    const UpdFeat& F = P.f[cur.feat];
+    if (F.max_chunks == 0) {           // a feature of another vector class: not this launch's
+      it = itn;
+      if (it < n_long) { cur = P.items[it]; piece_bags(P, cur, lane, bag, sc); }
+      continue;
     }
-  } else {
-    // ---- hot-row pieces: one warp per piece, rows staged with cp.async ------------------
-    float* stage = reinterpret_cast<float*>(s_dyn + (size_t)warp * kStageBytes);
-    int it = grab(0);
-    int itn = grab(0);
-    LongItem cur, nxt;
-    int bag[2], nbag[2];
-    float sc[2], nsc[2];
-    if (it < n_long) {
-      cur = P.items[it];
-      piece_bags(P, cur, lane, bag, sc);
+    const int log2g = F.log2g;
+    const int G = 1 << log2g;
+    const int ng = 32 >> log2g;        // groups per warp
+    const int gi = (int)lane >> log2g;
+    const int l = (int)lane & (G - 1);
+    const int dim = F.dim;
+    const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
+    int col[V];
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      col[v] = ((v << log2g) + l) * 4;
+      act[v] = col[v] < dim;
     }
-    while (it < n_long) {
-      const UpdFeat& F = P.f[cur.feat];
-      if (F.max_chunks == 0) {           // a feature of another vector class: not this launch's
-        it = itn;
-        itn = grab(0);
-        if (it < n_long) { cur = P.items[it]; piece_bags(P, cur, lane, bag, sc); }
-        continue;
-      }
-      const int log2g = F.log2g;
-      const int G = 1 << log2g;
-      const int ng = 32 >> log2g;        // groups per warp
-      const int gi = (int)lane >> log2g;
-      const int l = (int)lane & (G - 1);
-      const int dim = F.dim;
-      const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
-      int col[V];
-      bool act[V];
+    const int m = cur.count;
+    // (1) start the copies of all rows of the piece: group gi fetches rows gi, gi + ng, ...
+    for (int t0 = 0; t0 < m; t0 += ng) {   // warp-uniform trip count
+      const int j = t0 + gi;
+      const int b = __shfl_sync(0xffffffffu, bag[t0 >> 5], j & 31);
+      if (j < m) {
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        col[v] = ((v << log2g) + l) * 4;
-        act[v] = col[v] < dim;
+        for (int v = 0; v < V; ++v)
+          if (act[v]) cp_async16(stage + (size_t)j * dim + col[v], F.grad + (int64_t)b * F.grad_stride + col[v]);
       }
-      const int m = cur.count;
-      // (1) start the copies of all rows of the piece: group gi fetches rows gi, gi + ng, ...
-      for (int t0 = 0; t0 < m; t0 += ng) {   // warp-uniform trip count
-        const int j = t0 + gi;
-        const int b = __shfl_sync(0xffffffffu, bag[t0 >> 5], j & 31);
-        if (j < m) {
+    }
+    // (2) the next piece's descriptor travels meanwhile
+    if (itn < n_long) nxt = P.items[itn];
+    // (3) rows have landed
+    cp_async_wait_all();
+    __syncwarp();
+    // (4) the next piece's bags travel while this piece is added up
+    if (itn < n_long) piece_bags(P, nxt, lane, nbag, nsc);
+    // (5) group gi adds rows gi, gi + ng, ... in that order
+    float4 acc[V];
 #pragma unroll
-          for (int v = 0; v < V; ++v)
-            if (act[v]) cp_async16(stage + (size_t)j * dim + col[v], F.grad + (int64_t)b * F.grad_stride + col[v]);
-        }
+    for (int v = 0; v < V; ++v) acc[v] = f4_zero();
+    bool first = true;
+    for (int t0 = 0; t0 < m; t0 += ng) {
+      const int j = t0 + gi;
+      const float c = scaled ? __shfl_sync(0xffffffffu, sc[t0 >> 5], j & 31) : 1.0f;
+      if (j < m) {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (act[v]) {
+            float4 t = *reinterpret_cast<const float4*>(stage + (size_t)j * dim + col[v]);
+            if (scaled) t = f4_div_rn(t, c);
+            acc[v] = first ? t : f4_add_rn(acc[v], t);
+          }
+        first = false;
       }
-      // (2) the next piece's descriptor travels meanwhile
-      const int itn2 = grab(0);
-      if (itn < n_long) nxt = P.items[itn];
-      // (3) rows have landed
-      cp_async_wait_all();
+    }
+    __syncwarp();  // the stage may be overwritten by the next piece from here on
+    // group sums -> piece sum, fixed order: g0 += g(ng/2) ... (idle groups hold zeros)
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      for (int off = ng >> 1; off >= 1; off >>= 1) {
+        float4 y;
+        y.x = __shfl_down_sync(0xffffffffu, acc[v].x, off << log2g);
+        y.y = __shfl_down_sync(0xffffffffu, acc[v].y, off << log2g);
+        y.z = __shfl_down_sync(0xffffffffu, acc[v].z, off << log2g);
+        y.w = __shfl_down_sync(0xffffffffu, acc[v].w, off << log2g);
+        if (gi < off) acc[v] = f4_add_rn(acc[v], y);
+      }
+    bool last = false;
+    if (cur.np == 1) {
+      if (gi == 0) sink_row<V, OPT, MODE, FAST>(P, F, cur.key, cur.u, acc, col, act, oob);
+    } else {
+      // multi-piece run: park the piece sum; the warp arriving last adds all pieces in
+      // piece order (which warp that is does not change the order of the additions)
+      float* prow = P.part + (size_t)(cur.pbase + cur.piece) * P.part_stride;
+      if (gi == 0) {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (act[v]) *reinterpret_cast<float4*>(prow + col[v]) = acc[v];
+      }
+      __threadfence();
       __syncwarp();
-      // (4) the next piece's bags travel while this piece is added up
-      if (itn < n_long) piece_bags(P, nxt, lane, nbag, nsc);
-      // (5) group gi adds rows gi, gi + ng, ... in that order
-      float4 acc[V];
+      int old = 0;
+      if (lane == 0) old = atomicAdd(&P.tickets[cur.pbase], 1);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      last = (old == cur.np - 1);  // warp-uniform
+    }
+    if (last) {
+      __threadfence();
+      // group gi adds pieces gi, gi + ng, ...; the group sums are combined as above
+      const float* p0 = P.part + (size_t)cur.pbase * P.part_stride;
+      float4 tot[V];
 #pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] = f4_zero();
-      bool first = true;
-      for (int t0 = 0; t0 < m; t0 += ng) {
-        const int j = t0 + gi;
-        const float c = __shfl_sync(0xffffffffu, sc[t0 >> 5], j & 31);
-        if (j < m) {
+      for (int v = 0; v < V; ++v) tot[v] = f4_zero();
+      bool first2 = true;
+      for (int j0 = gi; j0 - gi < cur.np; j0 += ng * kBatch) {  // warp-uniform trip count
+        float4 x[kBatch][V];
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i)
 #pragma unroll
           for (int v = 0; v < V; ++v)
-            if (act[v]) {
-              float4 t = *reinterpret_cast<const float4*>(stage + (size_t)j * dim + col[v]);
-              if (scaled) t = f4_div_rn(t, c);
-              acc[v] = first ? t : f4_add_rn(acc[v], t);
-            }
-          first = false;
-        }
+            x[i][v] = (j0 + i * ng < cur.np && act[v])
+                          ? ld_cg_f4(reinterpret_cast<const float4*>(p0 + (size_t)(j0 + i * ng) * P.part_stride + col[v]))
+                          : f4_zero();
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i)
+          if (j0 + i * ng < cur.np) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) tot[v] = first2 ? x[i][v] : f4_add_rn(tot[v], x[i][v]);
+            first2 = false;
+          }
       }
-      __syncwarp();  // the stage may be overwritten by the next piece from here on
-      // group sums -> piece sum, fixed order: g0 += g(ng/2) ... (idle groups hold zeros)
 #pragma unroll
       for (int v = 0; v < V; ++v)
         for (int off = ng >> 1; off >= 1; off >>= 1) {
           float4 y;
-          y.x = __shfl_down_sync(0xffffffffu, acc[v].x, off << log2g);
-          y.y = __shfl_down_sync(0xffffffffu, acc[v].y, off << log2g);
-          y.z = __shfl_down_sync(0xffffffffu, acc[v].z, off << log2g);
-          y.w = __shfl_down_sync(0xffffffffu, acc[v].w, off << log2g);
-          if (gi < off) acc[v] = f4_add_rn(acc[v], y);
+          y.x = __shfl_down_sync(0xffffffffu, tot[v].x, off << log2g);
+          y.y = __shfl_down_sync(0xffffffffu, tot[v].y, off << log2g);
+          y.z = __shfl_down_sync(0xffffffffu, tot[v].z, off << log2g);
+          y.w = __shfl_down_sync(0xffffffffu, tot[v].w, off << log2g);
+          if (gi < off) tot[v] = f4_add_rn(tot[v], y);
         }
-      bool last = false;
-      if (cur.np == 1) {
-        if (gi == 0) sink_row<V, OPT, MODE, FAST>(P, F, cur.key, cur.u, acc, col, act, oob);
-      } else {
-        // multi-piece run: park the piece sum; the warp arriving last adds all pieces in
-        // piece order (which warp that is does not change the order of the additions)
-        float* prow = P.part + (size_t)(cur.pbase + cur.piece) * P.part_stride;
-        if (gi == 0) {
-#pragma unroll
-          for (int v = 0; v < V; ++v)
-            if (act[v]) *reinterpret_cast<float4*>(prow + col[v]) = acc[v];
-        }
-        __threadfence();
-        __syncwarp();
-        int old = 0;
-        if (lane == 0) old = atomicAdd(&P.tickets[cur.pbase], 1);
-        old = __shfl_sync(0xffffffffu, old, 0);
-        last = (old == cur.np - 1);  // warp-uniform
-      }
-      if (last) {
-        __threadfence();
-        // group gi adds pieces gi, gi + ng, ...; the group sums are combined as above
-        const float* p0 = P.part + (size_t)cur.pbase * P.part_stride;
-        float4 tot[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) tot[v] = f4_zero();
-        bool first2 = true;
-        for (int j0 = gi; j0 - gi < cur.np; j0 += ng * kBatch) {  // warp-uniform trip count
-          float4 x[kBatch][V];
-#pragma unroll
-          for (int i = 0; i < kBatch; ++i)
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-              x[i][v] = (j0 + i * ng < cur.np && act[v])
-                            ? ld_cg_f4(reinterpret_cast<const float4*>(p0 + (size_t)(j0 + i * ng) * P.part_stride + col[v]))
-                            : f4_zero();
-#pragma unroll
-          for (int i = 0; i < kBatch; ++i)
-            if (j0 + i * ng < cur.np) {
-#pragma unroll
-              for (int v = 0; v < V; ++v) tot[v] = first2 ? x[i][v] : f4_add_rn(tot[v], x[i][v]);
-              first2 = false;
-            }
-        }
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-          for (int off = ng >> 1; off >= 1; off >>= 1) {
-            float4 y;
-            y.x = __shfl_down_sync(0xffffffffu, tot[v].x, off << log2g);
-            y.y = __shfl_down_sync(0xffffffffu, tot[v].y, off << log2g);
-            y.z = __shfl_down_sync(0xffffffffu, tot[v].z, off << log2g);
-            y.w = __shfl_down_sync(0xffffffffu, tot[v].w, off << log2g);
-            if (gi < off) tot[v] = f4_add_rn(tot[v], y);
-          }
-        if (gi == 0) sink_row<V, OPT, MODE, FAST>(P, F, cur.key, cur.u, tot, col, act, oob);
-      }
-      cur = nxt;
-      bag[0] = nbag[0]; bag[1] = nbag[1];
-      sc[0] = nsc[0]; sc[1] = nsc[1];
-      it = itn;
-      itn = itn2;
+      if (gi == 0) sink_row<V, OPT, MODE, FAST>(P, F, cur.key, cur.u, tot, col, act, oob);
     }
+    cur = nxt;
+    bag[0] = nbag[0]; bag[1] = nbag[1];
+    sc[0] = nsc[0]; sc[1] = nsc[1];
+    it = itn;
   }
-  }  // round
   if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
 }
 
@@ -883,7 +808,7 @@ constexpr int kRadixBins = 1 << kRadixBits;
 
 // per-feature workspace layout (a function of nnz, dim and offsets != NULL only)
 struct UpdLayout {
-  size_t keysA, keysB, valsA, valsB, bagmap, ukey, ustart, uval, counts, end;
+  size_t keysA, keysB, valsA, valsB, bagmap, ukey, ustart, ubag4, counts, end;
   int log2g, V;
 };
 
@@ -897,7 +822,7 @@ static UpdLayout upd_layout(const hbUpdateFeature& f, size_t base) {
   L.bagmap = take(f.offsets ? 4 * n : 0);
   L.ukey = take(4 * n);
   L.ustart = take(4 * (n + 1));
-  L.uval = take(4 * n);
+  L.ubag4 = take(16 * n);
   L.counts = take(64);
   upd_shape(f.dim, &L.log2g, &L.V);
   L.end = o;
@@ -946,51 +871,74 @@ static SharedLayout shared_layout(size_t base, int nc, size_t total_tiles, size_
 
 static inline size_t run_tiles_of(int64_t nnz) { return (size_t)((nnz + kRunTile - 1) / kRunTile) + 1; }
 
-template <int V, int OPT, int MODE, bool FAST>
-static int launch_apply(const UpdParams& U, int max_short_ctas, cudaStream_t stream) {
-  (void)max_short_ctas;
-  const size_t smem = (size_t)(kUpdThreads / 32) * kStageBytes;
-  HB_CUDA_OK(cudaFuncSetAttribute(update_apply_kernel<V, OPT, MODE, FAST>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int V, int OPT, int MODE, bool FAST, int OCC>
+static int launch_short(const UpdParams& U, cudaStream_t stream) {
   int per_sm = 0;
   HB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &per_sm, update_apply_kernel<V, OPT, MODE, FAST>, kUpdThreads, smem));
+      &per_sm, update_short_kernel<V, OPT, MODE, FAST, OCC>, kUpdThreads, 0));
   const int grid = device_sm_count() * (per_sm > 0 ? per_sm : 1);
   KernelScope ks(HB_K_SPARSE_UPDATE, stream);
-  update_apply_kernel<V, OPT, MODE, FAST><<<grid, kUpdThreads, smem, stream>>>(U);
+  update_short_kernel<V, OPT, MODE, FAST, OCC><<<grid, kUpdThreads, 0, stream>>>(U);
+  HB_CUDA_OK(cudaGetLastError());
+  return HB_OK;
+}
+
+// which: 0 = short kernel, 1 = long kernel
+template <int V, int OPT, int MODE, bool FAST>
+static int launch_apply(const UpdParams& U, int which, cudaStream_t stream) {
+  int per_sm = 0;
+  if (which == 0) {
+    if constexpr (V == 1) {
+      static const int occ = [] { const char* e = getenv("HB_SHORT_OCC"); return e ? atoi(e) : 5; }();
+      if (occ == 4) return launch_short<V, OPT, MODE, FAST, 4>(U, stream);
+      if (occ == 6) return launch_short<V, OPT, MODE, FAST, 6>(U, stream);
+      return launch_short<V, OPT, MODE, FAST, 5>(U, stream);
+    } else {
+      return launch_short<V, OPT, MODE, FAST, (V == 2 ? 3 : 1)>(U, stream);
+    }
+  } else {
+    const size_t smem = (size_t)(kUpdThreads / 32) * kStageBytes;
+    HB_CUDA_OK(cudaFuncSetAttribute(update_long_kernel<V, OPT, MODE, FAST>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &per_sm, update_long_kernel<V, OPT, MODE, FAST>, kUpdThreads, smem));
+    const int grid = device_sm_count() * (per_sm > 0 ? per_sm : 1);
+    KernelScope ks(HB_K_UPDATE_LONG, stream);
+    update_long_kernel<V, OPT, MODE, FAST><<<grid, kUpdThreads, smem, stream>>>(U);
+  }
   HB_CUDA_OK(cudaGetLastError());
   return HB_OK;
 }
 
 template <int V, int MODE>
-static int launch_apply_opt(const UpdParams& U, int max_short_ctas, cudaStream_t stream) {
-  if (MODE == kModeEmit) return launch_apply<V, HB_OPT_SGD, MODE, false>(U, max_short_ctas, stream);
+static int launch_apply_opt(const UpdParams& U, int which, cudaStream_t stream) {
+  if (MODE == kModeEmit) return launch_apply<V, HB_OPT_SGD, MODE, false>(U, which, stream);
   switch (U.opt) {
     case HB_OPT_ADAGRAD:
-      return U.fast ? launch_apply<V, HB_OPT_ADAGRAD, MODE, true>(U, max_short_ctas, stream)
-                    : launch_apply<V, HB_OPT_ADAGRAD, MODE, false>(U, max_short_ctas, stream);
+      return U.fast ? launch_apply<V, HB_OPT_ADAGRAD, MODE, true>(U, which, stream)
+                    : launch_apply<V, HB_OPT_ADAGRAD, MODE, false>(U, which, stream);
     case HB_OPT_LAZY_ADAM:
-      return U.fast ? launch_apply<V, HB_OPT_LAZY_ADAM, MODE, true>(U, max_short_ctas, stream)
-                    : launch_apply<V, HB_OPT_LAZY_ADAM, MODE, false>(U, max_short_ctas, stream);
+      return U.fast ? launch_apply<V, HB_OPT_LAZY_ADAM, MODE, true>(U, which, stream)
+                    : launch_apply<V, HB_OPT_LAZY_ADAM, MODE, false>(U, which, stream);
     default:
-      return launch_apply<V, HB_OPT_SGD, MODE, false>(U, max_short_ctas, stream);
+      return launch_apply<V, HB_OPT_SGD, MODE, false>(U, which, stream);
   }
 }
 
-static int launch_apply_v(int V, bool emit, const UpdParams& U, int max_short_ctas, cudaStream_t stream) {
+static int launch_apply_v(int V, bool emit, const UpdParams& U, int which, cudaStream_t stream) {
   if (emit) {
     switch (V) {
-      case 1: return launch_apply_opt<1, kModeEmit>(U, max_short_ctas, stream);
-      case 2: return launch_apply_opt<2, kModeEmit>(U, max_short_ctas, stream);
-      case 4: return launch_apply_opt<4, kModeEmit>(U, max_short_ctas, stream);
-      default: return launch_apply_opt<8, kModeEmit>(U, max_short_ctas, stream);
+      case 1: return launch_apply_opt<1, kModeEmit>(U, which, stream);
+      case 2: return launch_apply_opt<2, kModeEmit>(U, which, stream);
+      case 4: return launch_apply_opt<4, kModeEmit>(U, which, stream);
+      default: return launch_apply_opt<8, kModeEmit>(U, which, stream);
     }
   }
   switch (V) {
-    case 1: return launch_apply_opt<1, kModeApply>(U, max_short_ctas, stream);
-    case 2: return launch_apply_opt<2, kModeApply>(U, max_short_ctas, stream);
-    case 4: return launch_apply_opt<4, kModeApply>(U, max_short_ctas, stream);
-    default: return launch_apply_opt<8, kModeApply>(U, max_short_ctas, stream);
+    case 1: return launch_apply_opt<1, kModeApply>(U, which, stream);
+    case 2: return launch_apply_opt<2, kModeApply>(U, which, stream);
+    case 4: return launch_apply_opt<4, kModeApply>(U, which, stream);
+    default: return launch_apply_opt<8, kModeApply>(U, which, stream);
   }
 }
 
@@ -1226,7 +1174,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         F.vals = reinterpret_cast<int32_t*>(base + (inA ? L[k].valsA : L[k].valsB));
         F.ukey = reinterpret_cast<uint32_t*>(base + L[k].ukey);
         F.ustart = reinterpret_cast<int32_t*>(base + L[k].ustart);
-        F.uval = reinterpret_cast<int32_t*>(base + L[k].uval);
+        F.ubag4 = reinterpret_cast<int4*>(base + L[k].ubag4);
         F.counts = reinterpret_cast<int32_t*>(base + L[k].counts);
         F.inv = ex ? ex->inv : nullptr;
         F.owner_start1 = ex ? ex->owner_start1 : nullptr;
@@ -1242,33 +1190,12 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         runs_kernel<<<grid, kUpdThreads, 0, stream>>>(R);
         HB_CUDA_OK(cudaGetLastError());
       }
-      // 4. queue of hot rows
-      QueueParams Q;
-      Q.long_count = reinterpret_cast<int32_t*>(base + S.long_count);
-      Q.items = reinterpret_cast<LongItem*>(base + S.items);
-      Q.status = d_status;
-      Q.item_cap = S.item_cap; Q.part_cap = S.part_cap;
-      Q.nfeats = nc;
-      int qctas = 0;
-      for (int k = 0; k < nc; ++k) {
-        const hbUpdateFeature& f = feats[c0 + k];
-        Q.f[k].ustart = reinterpret_cast<int32_t*>(base + L[k].ustart);
-        Q.f[k].ukey = reinterpret_cast<uint32_t*>(base + L[k].ukey);
-        Q.f[k].counts = reinterpret_cast<int32_t*>(base + L[k].counts);
-        Q.f[k].piece = piece_rows(f.dim);
-        Q.f[k].max_chunks = (int)((f.nnz + kUpdThreads - 1) / kUpdThreads);
-        qctas += Q.f[k].max_chunks;
-      }
-      if (qctas > 0) {
-        const int qgrid = qctas < maxg ? qctas : maxg;
-        KernelScope ks(HB_K_UPDATE_LONG, stream);
-        queue_kernel<<<qgrid, kUpdThreads, 0, stream>>>(Q);
-        HB_CUDA_OK(cudaGetLastError());
-      }
     }
 
-    // 4./5. fused duplicate-sum + sink, one launch pair per V class
+    // 4. fused duplicate-sum + sink: the short kernels of every vector class (they also
+    //    queue the hot rows), then the long kernels
     if (!(phases & kPhaseApply)) continue;
+    for (int which = 0; which < 2; ++which)
     for (int V = 1; V <= 8; V <<= 1) {
       UpdParams U;
       U.wait = wait ? *wait : WaitSpec{nullptr, 0, 0};
@@ -1280,8 +1207,6 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
       U.part = reinterpret_cast<float*>(base + S.part);
       U.tickets = reinterpret_cast<int32_t*>(base + S.tickets);
       U.item_cap = S.item_cap; U.part_cap = S.part_cap; U.part_stride = S.part_stride;
-      U.ticket_base = 2 + 2 * (V == 1 ? 0 : (V == 2 ? 1 : (V == 4 ? 2 : 3)));
-      U.nfeats = 0;
       U.opt = opt->kind;
       U.fast = (opt->flags & HB_OPT_FLAG_FAST_MATH) ? 1 : 0;
       U.lr = opt->lr;
@@ -1292,7 +1217,6 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         U.lr = (float)((double)opt->lr * sqrt(1.0 - pow((double)opt->beta2, t)) /
                        (1.0 - pow((double)opt->beta1, t)));
       }
-      int max_ctas = 0;
       bool any = false;
       U.nfeats = nc;  // queued pieces name features by their index in the chunk
       for (int k = 0; k < nc; ++k) {
@@ -1307,7 +1231,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         F.ukey = reinterpret_cast<uint32_t*>(base + L[k].ukey);
         F.ustart = reinterpret_cast<int32_t*>(base + L[k].ustart);
         F.counts = reinterpret_cast<int32_t*>(base + L[k].counts);
-        F.uval = reinterpret_cast<int32_t*>(base + L[k].uval);
+        F.ubag4 = reinterpret_cast<const int4*>(base + L[k].ubag4);
         F.vals = reinterpret_cast<int32_t*>(base + (inA ? L[k].valsA : L[k].valsB));
         F.pos2bag = (ex && ex->inv != nullptr && f.offsets != nullptr)
                         ? reinterpret_cast<const int32_t*>(base + L[k].bagmap) : nullptr;
@@ -1318,13 +1242,12 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         F.rows = f.rows; F.grad_stride = f.grad_stride;
         F.dim = f.dim; F.combiner = f.combiner;
         F.log2g = L[k].log2g;
-        const int uc = (32 >> L[k].log2g) * kNU;
-        F.max_chunks = sel ? (int)((f.nnz + uc - 1) / uc) : 0;  // 0: not this launch's vector class
+        const int ng = 32 >> L[k].log2g;
+        F.max_chunks = sel ? (int)((f.nnz + ng - 1) / ng) : 0;  // 0: not this launch's vector class
         F.piece = piece_rows(f.dim);
-        max_ctas += F.max_chunks;
       }
       if (!any) continue;
-      rc = launch_apply_v(V, is_emit, U, max_ctas, stream);
+      rc = launch_apply_v(V, is_emit, U, which, stream);
       if (rc != HB_OK) return rc;
       wait = nullptr;  // later launches are stream-ordered behind the first
     }
