@@ -28,7 +28,6 @@
 #include <stdlib.h>
 
 #include "bucket.cuh"
-#include "tma.cuh"
 #include "update.cuh"
 
 namespace hb {
@@ -61,7 +60,7 @@ struct UpdFeat {
   int32_t combiner;
   int32_t log2g;
   int32_t max_chunks;       // static bound of the number of warp units of this feature (0: not in this launch)
-  int32_t piece;            // entries per piece of a long run (kStageBytes of rows)
+  int32_t piece;            // entries per piece of a long run (kPieceBytes of rows)
 };
 
 struct LongItem {   // one piece of a hot row
@@ -82,6 +81,7 @@ struct UpdParams {
   float* part;              // [part_cap][part_stride] piece sums of multi-piece runs
   int32_t* tickets;         // [part_cap] arrival counters, indexed by the run's pbase
   int32_t item_cap, part_cap, part_stride;
+  int32_t ticket_idx;       // long kernel: its work ticket is long_count[ticket_idx] (one per vector class)
   int32_t nfeats;
   int32_t opt;
   int32_t fast;             // approximate sqrt/div (MUFU) instead of the IEEE sequence
@@ -395,23 +395,15 @@ __global__ void __launch_bounds__(kUpdThreads) runs_kernel(const __grid_constant
 //                  gradient rows are requested together.  Runs longer than kShortMax are
 //                  cut into pieces and queued (their groups do the queueing instead of
 //                  idling).
-//   long kernel  : one warp per queued piece, rows staged in shared memory with cp.async.
-constexpr int kStageBytes = 8192;              // bytes of gradient rows a warp stages per piece
-constexpr int kMaxPiece = 64;                  // rows per piece at most (two bag registers per lane)
+//   long kernel  : one warp per queued piece, kLongRows x 128-bit loads per lane in flight.
+constexpr int kPieceBytes = 16384;   // gradient bytes per hot-row piece
+constexpr int kMaxPiece = 128;       // entries per piece at most
 
 static inline int piece_rows(int dim) {
-  int p = kStageBytes / (dim * 4);
+  int p = kPieceBytes / (dim * 4);
   if (p > kMaxPiece) p = kMaxPiece;
-  if (p < 2) p = 2;
+  if (p < 8) p = 8;
   return p;
-}
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-               :: "r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 // run bounds, key and first bags of the unique row a group owns in warp unit `unit`
@@ -536,21 +528,10 @@ update_short_kernel(const __grid_constant__ UpdParams P) {
           }
         }
       }
-      for (int j0 = 0; j0 < M.len; j0 += NG) {
-        int bag[NG];
+      // entries j0 .. j0 + NG - 1 (bag < 0: no such entry), added in position order
+      auto batch = [&](int j0, const int (&bag)[NG]) {
         float sc[NG];
         float4 x[NG][V];
-#pragma unroll
-        for (int i = 0; i < NG; ++i) {
-          const int j = j0 + i;
-          int vv = -1;
-          if (j < M.len) {
-            if (j < 4) vv = (j == 0) ? M.b.x : (j == 1 ? M.b.y : (j == 2 ? M.b.z : M.b.w));
-            else vv = F.vals[M.s + j];
-            if (F.pos2bag != nullptr) vv = F.pos2bag[vv];
-          }
-          bag[i] = vv;
-        }
 #pragma unroll
         for (int i = 0; i < NG; ++i) {
           sc[i] = (scaled && bag[i] >= 0) ? bag_scale(F, bag[i]) : 1.0f;
@@ -570,6 +551,31 @@ update_short_kernel(const __grid_constant__ UpdParams P) {
               acc[v] = (j0 + i == 0) ? t : f4_add_rn(acc[v], t);
             }
           }
+      };
+      const int b4[4] = {M.b.x, M.b.y, M.b.z, M.b.w};
+      {  // first batch: its bags came with the run bounds
+        int bag[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+          bag[i] = (i < M.len) ? b4[i] : -1;
+          if (F.pos2bag != nullptr && bag[i] >= 0) bag[i] = F.pos2bag[bag[i]];
+        }
+        batch(0, bag);
+      }
+      for (int j0 = NG; j0 < M.len; j0 += NG) {
+        int bag[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+          const int j = j0 + i;
+          int vv = -1;
+          if (j < M.len) {
+            if (NG < 4 && j < 4) vv = (j == 1) ? b4[1] : (j == 2 ? b4[2] : b4[3]);
+            else vv = F.vals[M.s + j];
+            if (F.pos2bag != nullptr) vv = F.pos2bag[vv];
+          }
+          bag[i] = vv;
+        }
+        batch(j0, bag);
       }
       if constexpr (MODE == kModeApply) {
 #pragma unroll
@@ -591,53 +597,90 @@ update_short_kernel(const __grid_constant__ UpdParams P) {
   if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
 }
 
-// bags (and gradient scales) of a piece: lane r holds rows r and r + 32
-__device__ __forceinline__ void piece_bags(const UpdParams& P, const LongItem& it, unsigned lane,
-                                           int (&bag)[2], float (&sc)[2]) {
-  const UpdFeat& F = P.f[it.feat];
-  const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
+// Sum of the entries gi, gi + ng, ... of a piece, in that order: R gradient rows per lane
+// in flight (128-bit loads), the bags of the next batch are requested before the rows
+// of the current one are consumed.
+template <int V, int R, bool SCALED>
+__device__ __forceinline__ void piece_sum(const UpdFeat& F, const LongItem& cur, int ng, int gi,
+                                          const int (&col)[V], const bool (&act)[V], float4 (&acc)[V]) {
+  const int m = cur.count;
+  const int step = ng * R;
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int j = r * 32 + (int)lane;
-    bag[r] = j < it.count ? entry_bag(F, it.start + j) : 0;
-    sc[r] = (scaled && j < it.count) ? bag_scale(F, bag[r]) : 1.0f;
+  for (int v = 0; v < V; ++v) acc[v] = f4_zero();
+  bool first = true;
+  int bag[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int j = r * ng + gi;
+    bag[r] = j < m ? entry_bag(F, cur.start + j) : 0;
+  }
+  for (int t0 = 0; t0 < m; t0 += step) {
+    float4 x[R][V];
+    float sc[SCALED ? R : 1];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool valid = t0 + r * ng + gi < m;
+      if constexpr (SCALED) sc[r] = valid ? bag_scale(F, bag[r]) : 1.0f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        x[r][v] = f4_zero();
+        if (valid && act[v])
+          x[r][v] = ld_nc_f4(reinterpret_cast<const float4*>(F.grad + (int64_t)bag[r] * F.grad_stride + col[v]));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {   // bags of the next batch
+      const int j = t0 + step + r * ng + gi;
+      bag[r] = j < m ? entry_bag(F, cur.start + j) : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (t0 + r * ng + gi < m) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float4 t = x[r][v];
+          if constexpr (SCALED) t = f4_div_rn(t, sc[r]);
+          acc[v] = first ? t : f4_add_rn(acc[v], t);
+        }
+        first = false;
+      }
   }
 }
 
-// Hot rows: one warp per queued piece (static round-robin), rows staged with cp.async.
+// Hot rows: one warp per queued piece (dynamic tickets: pieces differ in length).  Group
+// gi of the warp adds entries gi, gi + ng, ... of the piece in that order, kLongRows
+// gradient rows per lane in flight in registers (128-bit loads; the bags of the next
+// batch travel while the rows of the current one do); the group sums are combined in a
+// fixed shuffle tree.  Multi-piece runs park piece sums in global memory and the warp
+// that arrives last adds them in piece order.
 template <int V, int OPT, int MODE, bool FAST>
-__global__ void __launch_bounds__(kUpdThreads, (V == 1 ? 3 : (V == 2 ? 2 : 1)))
+__global__ void __launch_bounds__(kUpdThreads, (V == 1 ? 3 : 2))
 update_long_kernel(const __grid_constant__ UpdParams P) {
-  extern __shared__ __align__(128) unsigned char s_dyn[];  // [warps][kStageBytes]
-  constexpr int kBatch = (V == 1) ? 8 : (V == 2 ? 4 : 2);  // partial rows in flight (final combine)
+  constexpr int R = (V == 1) ? 8 : (V == 2 ? 4 : (V == 4 ? 2 : 1));  // rows in flight per group
   const unsigned lane = lane_id();
-  const int warp = threadIdx.x >> 5;
   int n_long = P.long_count[0];
   if (n_long > P.item_cap) n_long = P.item_cap;
-  const int nwarps = gridDim.x * (kUpdThreads / 32);
   bool oob = false;
-  float* stage = reinterpret_cast<float*>(s_dyn + (size_t)warp * kStageBytes);
-  int it = blockIdx.x * (kUpdThreads / 32) + warp;
-  LongItem cur, nxt;
-  int bag[2], nbag[2];
-  float sc[2], nsc[2];
-  if (it < n_long) {
-    cur = P.items[it];
-    piece_bags(P, cur, lane, bag, sc);
-  }
+  auto grab = [&]() -> int {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(&P.long_count[P.ticket_idx], 1);
+    return __shfl_sync(0xffffffffu, v, 0);
+  };
+  int it = grab();
+  int itn = grab();
   while (it < n_long) {
-    const int itn = it + nwarps;
+    const LongItem cur = P.items[it];
+    const int itn2 = grab();   // two tickets ahead: the atomic's latency is never exposed
     const UpdFeat& F = P.f[cur.feat];
-    if (F.max_chunks == 0) {           // a feature of another vector class: not this launch's
+    if (F.max_chunks == 0) {   // a feature of another vector class: not this launch's
       it = itn;
-      if (it < n_long) { cur = P.items[it]; piece_bags(P, cur, lane, bag, sc); }
+      itn = itn2;
       continue;
     }
     const int log2g = F.log2g;
-    const int G = 1 << log2g;
     const int ng = 32 >> log2g;        // groups per warp
     const int gi = (int)lane >> log2g;
-    const int l = (int)lane & (G - 1);
+    const int l = (int)lane & ((1 << log2g) - 1);
     const int dim = F.dim;
     const bool scaled = F.combiner != HB_SUM && F.offsets != nullptr;
     int col[V];
@@ -647,44 +690,9 @@ update_long_kernel(const __grid_constant__ UpdParams P) {
       col[v] = ((v << log2g) + l) * 4;
       act[v] = col[v] < dim;
     }
-    const int m = cur.count;
-    // (1) start the copies of all rows of the piece: group gi fetches rows gi, gi + ng, ...
-    for (int t0 = 0; t0 < m; t0 += ng) {   // warp-uniform trip count
-      const int j = t0 + gi;
-      const int b = __shfl_sync(0xffffffffu, bag[t0 >> 5], j & 31);
-      if (j < m) {
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-          if (act[v]) cp_async16(stage + (size_t)j * dim + col[v], F.grad + (int64_t)b * F.grad_stride + col[v]);
-      }
-    }
-    // (2) the next piece's descriptor travels meanwhile
-    if (itn < n_long) nxt = P.items[itn];
-    // (3) rows have landed
-    cp_async_wait_all();
-    __syncwarp();
-    // (4) the next piece's bags travel while this piece is added up
-    if (itn < n_long) piece_bags(P, nxt, lane, nbag, nsc);
-    // (5) group gi adds rows gi, gi + ng, ... in that order
     float4 acc[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = f4_zero();
-    bool first = true;
-    for (int t0 = 0; t0 < m; t0 += ng) {
-      const int j = t0 + gi;
-      const float c = scaled ? __shfl_sync(0xffffffffu, sc[t0 >> 5], j & 31) : 1.0f;
-      if (j < m) {
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-          if (act[v]) {
-            float4 t = *reinterpret_cast<const float4*>(stage + (size_t)j * dim + col[v]);
-            if (scaled) t = f4_div_rn(t, c);
-            acc[v] = first ? t : f4_add_rn(acc[v], t);
-          }
-        first = false;
-      }
-    }
-    __syncwarp();  // the stage may be overwritten by the next piece from here on
+    if (scaled) piece_sum<V, (R > 1 ? R / 2 : 1), true>(F, cur, ng, gi, col, act, acc);
+    else piece_sum<V, R, false>(F, cur, ng, gi, col, act, acc);
     // group sums -> piece sum, fixed order: g0 += g(ng/2) ... (idle groups hold zeros)
 #pragma unroll
     for (int v = 0; v < V; ++v)
@@ -723,17 +731,17 @@ update_long_kernel(const __grid_constant__ UpdParams P) {
 #pragma unroll
       for (int v = 0; v < V; ++v) tot[v] = f4_zero();
       bool first2 = true;
-      for (int j0 = gi; j0 - gi < cur.np; j0 += ng * kBatch) {  // warp-uniform trip count
-        float4 x[kBatch][V];
+      for (int j0 = gi; j0 - gi < cur.np; j0 += ng * R) {  // warp-uniform trip count
+        float4 x[R][V];
 #pragma unroll
-        for (int i = 0; i < kBatch; ++i)
+        for (int i = 0; i < R; ++i)
 #pragma unroll
           for (int v = 0; v < V; ++v)
             x[i][v] = (j0 + i * ng < cur.np && act[v])
                           ? ld_cg_f4(reinterpret_cast<const float4*>(p0 + (size_t)(j0 + i * ng) * P.part_stride + col[v]))
                           : f4_zero();
 #pragma unroll
-        for (int i = 0; i < kBatch; ++i)
+        for (int i = 0; i < R; ++i)
           if (j0 + i * ng < cur.np) {
 #pragma unroll
             for (int v = 0; v < V; ++v) tot[v] = first2 ? x[i][v] : f4_add_rn(tot[v], x[i][v]);
@@ -752,10 +760,8 @@ update_long_kernel(const __grid_constant__ UpdParams P) {
         }
       if (gi == 0) sink_row<V, OPT, MODE, FAST>(P, F, cur.key, cur.u, tot, col, act, oob);
     }
-    cur = nxt;
-    bag[0] = nbag[0]; bag[1] = nbag[1];
-    sc[0] = nsc[0]; sc[1] = nsc[1];
     it = itn;
+    itn = itn2;
   }
   if (oob) raise_status(P.status, HB_STATUS_ID_OUT_OF_RANGE);
 }
@@ -889,7 +895,7 @@ static int launch_apply(const UpdParams& U, int which, cudaStream_t stream) {
   int per_sm = 0;
   if (which == 0) {
     if constexpr (V == 1) {
-      static const int occ = [] { const char* e = getenv("HB_SHORT_OCC"); return e ? atoi(e) : 5; }();
+      static const int occ = [] { const char* e = getenv("HB_SHORT_OCC"); return e ? atoi(e) : 4; }();
       if (occ == 4) return launch_short<V, OPT, MODE, FAST, 4>(U, stream);
       if (occ == 6) return launch_short<V, OPT, MODE, FAST, 6>(U, stream);
       return launch_short<V, OPT, MODE, FAST, 5>(U, stream);
@@ -897,14 +903,11 @@ static int launch_apply(const UpdParams& U, int which, cudaStream_t stream) {
       return launch_short<V, OPT, MODE, FAST, (V == 2 ? 3 : 1)>(U, stream);
     }
   } else {
-    const size_t smem = (size_t)(kUpdThreads / 32) * kStageBytes;
-    HB_CUDA_OK(cudaFuncSetAttribute(update_long_kernel<V, OPT, MODE, FAST>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &per_sm, update_long_kernel<V, OPT, MODE, FAST>, kUpdThreads, smem));
+        &per_sm, update_long_kernel<V, OPT, MODE, FAST>, kUpdThreads, 0));
     const int grid = device_sm_count() * (per_sm > 0 ? per_sm : 1);
     KernelScope ks(HB_K_UPDATE_LONG, stream);
-    update_long_kernel<V, OPT, MODE, FAST><<<grid, kUpdThreads, smem, stream>>>(U);
+    update_long_kernel<V, OPT, MODE, FAST><<<grid, kUpdThreads, 0, stream>>>(U);
   }
   HB_CUDA_OK(cudaGetLastError());
   return HB_OK;
@@ -1207,6 +1210,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
       U.part = reinterpret_cast<float*>(base + S.part);
       U.tickets = reinterpret_cast<int32_t*>(base + S.tickets);
       U.item_cap = S.item_cap; U.part_cap = S.part_cap; U.part_stride = S.part_stride;
+      U.ticket_idx = 2 + (V == 1 ? 0 : (V == 2 ? 1 : (V == 4 ? 2 : 3)));
       U.opt = opt->kind;
       U.fast = (opt->flags & HB_OPT_FLAG_FAST_MATH) ? 1 : 0;
       U.lr = opt->lr;
