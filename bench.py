@@ -61,15 +61,18 @@ def table_sizes(args):
   return s
 
 
-def gen_ids_numpy(rng, n, vocab, dist, alpha):
-  """Bounded power-law ranks by inverse CDF, scrambled over the vocabulary."""
+def gen_ids_numpy(rng, n, vocab, dist, alpha, salt=0):
+  """Bounded power-law ranks by inverse CDF, scrambled over the vocabulary.  `salt`
+  (the feature index) shifts the scramble, so the hottest id of every feature is a
+  different row -- and, row-sharded, a different owner rank (salt 0 would make rank 0
+  the owner of the hottest row of EVERY table)."""
   if dist == 'uniform' or vocab <= 2:
     return rng.randint(0, vocab, n).astype(np.int64)
   u = rng.random_sample(n)
   a = 1.0 - alpha
   rank = np.floor(((vocab ** a - 1.0) * u + 1.0) ** (1.0 / a)).astype(np.int64)
   rank = np.clip(rank, 1, vocab) - 1
-  return (rank * 2654435761) % vocab
+  return (rank * 2654435761 + (salt * 0x9E3779B1) % vocab) % vocab
 
 
 class ClockSampler:
@@ -142,7 +145,7 @@ def cpu_arm(args, sizes, dim, steps, warmup, rank0_only_note=''):
   tables = [np.zeros((n, dim), np.float32) for n in csizes]       # lazily paged
   accs = [np.zeros((n, dim), np.float32) for n in csizes] if args.mode == 'train' else None
   nb = min(NUM_BATCHES, 2)
-  batches = [[gen_ids_numpy(rng, B, n, args.dist, args.alpha) for n in csizes] for _ in range(nb)]
+  batches = [[gen_ids_numpy(rng, B, n, args.dist, args.alpha, salt=k) for k, n in enumerate(csizes)] for _ in range(nb)]
   offsets = np.arange(B + 1, dtype=np.int64)
   grad = rng.randn(B, F * dim).astype(np.float32)
   out = np.empty((B, F * dim), np.float32)
@@ -309,7 +312,7 @@ def run_ours(args):
   rng = np.random.RandomState(1234 + rank)
   h_batches = []
   for _ in range(NUM_BATCHES):
-    blk = np.stack([gen_ids_numpy(rng, B, n, args.dist, args.alpha) for n in sizes])  # [F, B]
+    blk = np.stack([gen_ids_numpy(rng, B, n, args.dist, args.alpha, salt=k) for k, n in enumerate(sizes)])  # [F, B]
     h_batches.append(torch.from_numpy(blk).pin_memory())
   d_batches = [hb_.to(dev) for hb_ in h_batches]
   grad = torch.randn(B, F * dim, device=dev, generator=g)
@@ -417,7 +420,7 @@ def run_ours(args):
     uniq = {k: 0.0 for k in shard_feats}
     gens = [np.random.RandomState(1234 + r) for r in range(world)]
     for _ in range(NUM_BATCHES):
-      blks = [np.stack([gen_ids_numpy(gr, B, n, args.dist, args.alpha) for n in sizes]) for gr in gens]
+      blks = [np.stack([gen_ids_numpy(gr, B, n, args.dist, args.alpha, salt=k) for k, n in enumerate(sizes)]) for gr in gens]
       for k in shard_feats:
         mine = np.concatenate([blk[k][blk[k] % world == rank] for blk in blks])
         recv[k] += len(mine) / NUM_BATCHES

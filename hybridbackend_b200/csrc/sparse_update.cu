@@ -3,22 +3,21 @@
 //
 // Pipeline (all features of the group per launch):
 //   1. bag_of_position : CSR features only -- bag index of every id position.
-//   2. LSD radix sort  : (row key, bag) pairs grouped by key, 9-bit digits, stable,
-//                        so entries of a row stay in position order (bucket.cuh).
-//   3. runs kernel     : one scan over the sorted keys -> unique keys, the first
-//                        entry of every run, the unique count (all on device).
-//   4. short kernel    : work item = one UNIQUE row.  A sub-warp group of G lanes
-//                        (G*4 floats = one row) loads the run bounds, sums the
-//                        gradient rows of the run in position order in registers and
-//                        applies the optimizer once (one read-modify-write of the
-//                        table row and its slot rows).  No cross-thread state, no
-//                        shuffles, no barriers.  Runs longer than kShortMax are
-//                        queued instead.
-//   5. long kernel     : hot rows.  A queued run is cut into pieces of kPiece
-//                        entries, one warp per piece: its groups sum interleaved
-//                        entries, the group sums are combined in a fixed shuffle
-//                        tree; multi-piece runs park piece sums in global memory
-//                        and the warp that arrives last adds them in piece order.
+//   2. cluster sort    : ONE launch, a cluster of 8 CTAs per feature (cluster_sort.cuh):
+//                        stable LSD radix sort of (row key, bag) pairs, 9-bit digits, the
+//                        passes separated by cluster barriers; then, in the same kernel,
+//                        one scan over the sorted keys -> unique keys, the first entry and
+//                        the first four bags of every run, the unique count (on device).
+//   3. short kernel    : work item = one UNIQUE row.  A sub-warp group of G lanes
+//                        (G*4 floats = one row) sums the gradient rows of the run in
+//                        position order in registers and applies the optimizer once (one
+//                        read-modify-write of the table row and its slot rows).  No
+//                        cross-thread state, no shuffles, no barriers.  Runs longer than
+//                        kShortMax are cut into pieces of piece_rows(dim) entries and queued.
+//   4. long kernel     : hot rows, one warp per queued piece: its groups sum interleaved
+//                        entries (8 rows per lane in flight), the group sums are combined
+//                        in a fixed shuffle tree; multi-piece runs park piece sums in global
+//                        memory and the warp that arrives last adds them in piece order.
 // The order of every floating-point addition is a fixed function of the run length
 // => bit-reproducible (test_determinism), whatever the scheduling.
 //
@@ -27,13 +26,16 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "bucket.cuh"
+#include "cluster_sort.cuh"
 #include "update.cuh"
 
 namespace hb {
 
 constexpr int kUpdThreads = 256;
-constexpr int kMaxUpdFeats = 96;
+constexpr int kMaxUpdFeats = kCsMaxFeats;
 constexpr int kShortMax = 16;   // runs up to this many entries are summed by one group
 
 enum { kModeApply = 0, kModeEmit = 1 };
@@ -245,143 +247,6 @@ __device__ __forceinline__ int seg_find(const int* s_begin, int nsegs, int unit)
     if (s_begin[mid] <= unit) lo = mid; else hi = mid - 1;
   }
   return lo;
-}
-
-// ---- 3. runs ----------------------------------------------------------------------------
-constexpr int kRunItems = 16;
-constexpr int kRunTile = kUpdThreads * kRunItems;  // 4096
-
-struct RunFeat {
-  const uint32_t* keys;   // sorted
-  const int32_t* vals;
-  uint32_t* ukey;
-  int32_t* ustart;
-  int4* ubag4;            // values (bag / position) of the first four entries of every run
-  int32_t* counts;        // [0] = U, [1] = valid entries
-  int32_t* inv;           // may be nullptr
-  int32_t* owner_start1;  // may be nullptr
-  const int32_t* n_dev;
-  int32_t n;
-  int32_t lbits;
-};
-
-struct RunParams {
-  RunFeat f[kMaxUpdFeats];
-  uint32_t* status;   // [sum of static tiles + nfeats], zeroed
-  uint32_t* ticket;   // zeroed
-  int32_t* d_status;
-  int32_t nfeats;
-};
-
-__device__ __forceinline__ int run_len(const RunFeat& F) {
-  if (F.n_dev == nullptr) return F.n;
-  const int d = *F.n_dev;
-  return d < 0 ? 0 : (d < F.n ? d : F.n);
-}
-
-__global__ void __launch_bounds__(kUpdThreads) runs_kernel(const __grid_constant__ RunParams P) {
-  __shared__ int s_begin[kMaxUpdFeats + 1];
-  __shared__ int32_t s_scan[kBucketWarps];
-  __shared__ int s_tile;
-  __shared__ int32_t s_pre;
-  const int tid = threadIdx.x;
-  int units = 0;
-  if (tid < P.nfeats) {
-    const int n = run_len(P.f[tid]);
-    units = (n + kRunTile - 1) / kRunTile;
-    if (units < 1) units = 1;  // an empty feature still publishes U = 0
-  }
-  const int total = seg_scan(P.nfeats, units, s_begin);
-  bool oob = false;
-  while (true) {
-    __syncthreads();
-    if (tid == 0) s_tile = (int)atomicAdd(P.ticket, 1u);
-    __syncthreads();
-    const int tile = s_tile;
-    if (tile >= total) break;
-    const int fi = seg_find(s_begin, P.nfeats, tile);
-    const RunFeat& F = P.f[fi];
-    const int t = tile - s_begin[fi];
-    const int n = run_len(F);
-    const int i0 = t * kRunTile + tid * kRunItems;
-    // k[0] = key of the entry before mine, k[1..16] mine, k[17] the one after
-    uint32_t k[kRunItems + 2];
-    if (i0 + kRunItems <= n) {  // 64-byte aligned run of 16 keys: four 128-bit loads
-      const uint4* p = reinterpret_cast<const uint4*>(F.keys + i0);
-#pragma unroll
-      for (int q = 0; q < kRunItems / 4; ++q) {
-        const uint4 v = p[q];
-        k[1 + 4 * q] = v.x; k[2 + 4 * q] = v.y; k[3 + 4 * q] = v.z; k[4 + 4 * q] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < kRunItems; ++j) k[j + 1] = (i0 + j < n) ? F.keys[i0 + j] : 0xFFFFFFFFu;
-    }
-    k[0] = (i0 > 0 && i0 - 1 < n) ? F.keys[i0 - 1] : 0xFFFFFFFFu;
-    k[kRunItems + 1] = (i0 + kRunItems < n) ? F.keys[i0 + kRunItems] : 0xFFFFFFFFu;
-    uint32_t heads = 0;
-#pragma unroll
-    for (int j = 0; j < kRunItems; ++j) {
-      const int i = i0 + j;
-      const bool valid = i < n && k[j + 1] < 0xFFFFFFFEu;
-      if (i < n && k[j + 1] == 0xFFFFFFFEu) oob = true;
-      if (valid && (i == 0 || k[j + 1] != k[j])) heads |= 1u << j;
-    }
-    int32_t tile_total;
-    const int32_t excl = block_excl_scan(__popc(heads), s_scan, &tile_total);
-    if (tid == 0)
-      *reinterpret_cast<volatile uint32_t*>(&P.status[tile]) = (uint32_t)tile_total | kReady;
-    // uniques in the preceding tiles of this feature: summed by the first warp
-    if (tid < 32) {
-      int32_t pre = 0;
-      for (int tp = tid; tp < t; tp += 32) {
-        const uint32_t* w = P.status + s_begin[fi] + tp;
-        uint32_t v = ld_volatile_u32(w);
-        while (!(v & kReady)) v = ld_volatile_u32(w);
-        pre += (int32_t)(v & ~kReady);
-      }
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, off);
-      if (tid == 0) s_pre = pre;
-    }
-    __syncthreads();
-    int u = s_pre + excl;  // index the next head of this thread gets
-#pragma unroll
-    for (int j = 0; j < kRunItems; ++j) {
-      const int i = i0 + j;
-      if (i >= n) break;
-      const bool valid = k[j + 1] < 0xFFFFFFFEu;
-      if ((heads >> j) & 1u) {
-        F.ukey[u] = k[j + 1];
-        F.ustart[u] = i;
-        {  // first four values of the run (entries past its end are never used)
-          int4 b4;
-          b4.x = F.vals[i];
-          b4.y = (i + 1 < n) ? F.vals[i + 1] : 0;
-          b4.z = (i + 2 < n) ? F.vals[i + 2] : 0;
-          b4.w = (i + 3 < n) ? F.vals[i + 3] : 0;
-          F.ubag4[u] = b4;
-        }
-        if (F.owner_start1 != nullptr) {
-          const uint32_t own = k[j + 1] >> F.lbits;
-          if (i == 0 || (k[j] >> F.lbits) != own) F.owner_start1[own] = u + 1;
-        }
-        ++u;
-      }
-      if (F.inv != nullptr) F.inv[F.vals[i]] = valid ? u - 1 : -1;
-      if (valid && (i + 1 >= n || k[j + 2] >= 0xFFFFFFFEu)) {  // last valid entry of the feature
-        F.ustart[u] = i + 1;
-        F.counts[0] = u;
-        F.counts[1] = i + 1;
-      }
-    }
-    if (t == 0 && tid == 0 && (n == 0 || k[1] >= 0xFFFFFFFEu)) {  // no valid entry at all
-      F.ustart[0] = 0;
-      F.counts[0] = 0;
-      F.counts[1] = 0;
-    }
-  }
-  if (oob) raise_status(P.d_status, HB_STATUS_ID_OUT_OF_RANGE);
 }
 
 // ---- 4. apply ---------------------------------------------------------------------------
@@ -814,7 +679,7 @@ constexpr int kRadixBins = 1 << kRadixBits;
 
 // per-feature workspace layout (a function of nnz, dim and offsets != NULL only)
 struct UpdLayout {
-  size_t keysA, keysB, valsA, valsB, bagmap, ukey, ustart, ubag4, counts, end;
+  size_t keysA, keysB, valsA, valsB, bagmap, ukey, ustart, ubag4, counts, cs_hist, cs_uniq, end;
   int log2g, V;
 };
 
@@ -830,16 +695,16 @@ static UpdLayout upd_layout(const hbUpdateFeature& f, size_t base) {
   L.ustart = take(4 * (n + 1));
   L.ubag4 = take(16 * n);
   L.counts = take(64);
+  L.cs_hist = take(sizeof(uint32_t) * kCsBins * (size_t)cs_tiles(f.nnz));
+  L.cs_uniq = take(sizeof(int32_t) * ((size_t)cs_tiles(f.nnz) + 1));
   upd_shape(f.dim, &L.log2g, &L.V);
   L.end = o;
   return L;
 }
 
-// chunk-shared scratch behind the per-feature regions
+// chunk-shared scratch behind the per-feature regions: the hot-row queue
 struct SharedLayout {
-  // zeroed per sort: bucket scratch, run status/ticket, hot-row queue counters and tickets
-  size_t zero_sort, zero_sort_bytes;
-  size_t bucket, run_status, run_ticket;
+  size_t zero_sort, zero_sort_bytes;   // zeroed by the sort kernel: queue counters and tickets
   size_t long_count, tickets;
   size_t items, part;
   size_t end;
@@ -854,15 +719,11 @@ static inline size_t long_items_of(int64_t nnz, int dim) {
 }
 static inline size_t long_parts_of(int64_t nnz, int dim) { return (size_t)(2 * (nnz / piece_rows(dim)) + 2); }
 
-static SharedLayout shared_layout(size_t base, int nc, size_t total_tiles, size_t run_tiles,
-                                  size_t item_cap, size_t part_cap, int max_dim) {
+static SharedLayout shared_layout(size_t base, size_t item_cap, size_t part_cap, int max_dim) {
   SharedLayout S;
   size_t o = align_up(base, 256);
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
   S.zero_sort = o;
-  S.bucket = take(bucket_scratch_words(nc, total_tiles, kRadixBins, kMaxPasses) * sizeof(uint32_t));
-  S.run_status = take((run_tiles + (size_t)nc + 1) * sizeof(uint32_t));
-  S.run_ticket = take(64);
   S.item_cap = (int)item_cap;
   S.part_cap = (int)part_cap;
   S.part_stride = (max_dim + 3) / 4 * 4;
@@ -875,7 +736,6 @@ static SharedLayout shared_layout(size_t base, int nc, size_t total_tiles, size_
   return S;
 }
 
-static inline size_t run_tiles_of(int64_t nnz) { return (size_t)((nnz + kRunTile - 1) / kRunTile) + 1; }
 
 template <int V, int OPT, int MODE, bool FAST, int OCC>
 static int launch_short(const UpdParams& U, cudaStream_t stream) {
@@ -945,6 +805,17 @@ static int launch_apply_v(int V, bool emit, const UpdParams& U, int which, cudaS
   }
 }
 
+// debug: HB_CS_TIMING=1 allocates a small device buffer the sort kernel stamps
+static unsigned long long* g_cs_timing = nullptr;
+static unsigned long long* cs_timing_buffer() {
+  static const bool on = [] { const char* e = getenv("HB_CS_TIMING"); return e != nullptr && e[0] == '1'; }();
+  if (on && g_cs_timing == nullptr) {
+    if (cudaMalloc(reinterpret_cast<void**>(&g_cs_timing), 64 * 8) != cudaSuccess) g_cs_timing = nullptr;
+    else cudaMemset(g_cs_timing, 0, 64 * 8);
+  }
+  return g_cs_timing;
+}
+
 static int validate_upd(int k, const hbUpdateFeature& f, const hbOptimizer* opt, int phases,
                         const UpdExtra* ex, bool emit) {
   HB_REQUIRE(f.dim >= 4 && f.dim % 4 == 0 && f.dim <= 1024,
@@ -986,19 +857,17 @@ size_t sparse_update_workspace_bytes(int n, const hbUpdateFeature* feats) {
   size_t o = 0, shared_total = 0;
   for (int c0 = 0; c0 < n; c0 += kMaxUpdFeats) {
     const int nc = (n - c0 < kMaxUpdFeats) ? n - c0 : kMaxUpdFeats;
-    size_t tiles = 0, rtiles = 0, items = 64, parts = 64;
+    size_t items = 64, parts = 64;
     int max_dim = 4;
     for (int k = 0; k < nc; ++k) {
       const hbUpdateFeature& f = feats[c0 + k];
       o = upd_layout(f, o).end;
-      tiles += bucket_tiles(f.nnz);
-      rtiles += run_tiles_of(f.nnz);
       items += long_items_of(f.nnz, f.dim);
       parts += long_parts_of(f.nnz, f.dim);
       if (f.dim > max_dim) max_dim = f.dim;
     }
     // one shared region per chunk: the hot-row queue lives from the sort phase to the apply
-    shared_total += align_up(shared_layout(0, nc, tiles, rtiles, items, parts, max_dim).end, 256);
+    shared_total += align_up(shared_layout(0, items, parts, max_dim).end, 256);
   }
   return align_up(o, 256) + shared_total + 256;
 }
@@ -1037,15 +906,13 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
     UpdLayout L[kMaxUpdFeats];
     int passes[kMaxUpdFeats];
     size_t o = off;
-    size_t total_tiles = 0, total_rtiles = 0, total_items = 64, total_parts = 64;
+    size_t total_items = 64, total_parts = 64;
     int max_passes = 0, max_dim = 4;
     for (int k = 0; k < nc; ++k) {
       const hbUpdateFeature& f = feats[c0 + k];
       const UpdExtra* ex = extras ? &extras[c0 + k] : nullptr;
       L[k] = upd_layout(f, o);
       o = L[k].end;
-      total_tiles += (size_t)bucket_tiles(f.nnz);
-      total_rtiles += run_tiles_of(f.nnz);
       total_items += long_items_of(f.nnz, f.dim);
       total_parts += long_parts_of(f.nnz, f.dim);
       if (f.dim > max_dim) max_dim = f.dim;
@@ -1061,7 +928,7 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
       }
     }
     off = o;
-    const SharedLayout S = shared_layout(shared_off, nc, total_tiles, total_rtiles, total_items, total_parts, max_dim);
+    const SharedLayout S = shared_layout(shared_off, total_items, total_parts, max_dim);
     shared_off = align_up(S.end, 256);
 
     if (phases & kPhaseSort) {
@@ -1087,94 +954,32 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         HB_CUDA_OK(cudaGetLastError());
       }
 
-      // 2. LSD radix sort: one memset, one histogram kernel over the inputs (all
-      //    digit positions), then one kernel per digit position; feature k takes
-      //    part in pass p iff p < passes[k]
-      HB_CUDA_OK(cudaMemsetAsync(base + S.zero_sort, 0, S.zero_sort_bytes, stream));
-      if (max_passes > 0) {
-        BucketScratch sc = bucket_scratch_carve(reinterpret_cast<uint32_t*>(base + S.bucket), nc,
-                                                total_tiles, kRadixBins, max_passes);
-        for (int p = -1; p < max_passes; ++p) {  // p == -1: histogram launch
-          BucketParams bp;
-          bp.nsegs = 0;
-          int tiles = 0;
-          for (int k = 0; k < nc; ++k) {
-            const hbUpdateFeature& f = feats[c0 + k];
-            const UpdExtra* ex = extras ? &extras[c0 + k] : nullptr;
-            if (f.nnz == 0 || (p >= 0 && p >= passes[k])) continue;
-            BucketSeg& s = bp.seg[bp.nsegs++];
-            uint32_t* kA = reinterpret_cast<uint32_t*>(base + L[k].keysA);
-            uint32_t* kB = reinterpret_cast<uint32_t*>(base + L[k].keysB);
-            int32_t* vA = reinterpret_cast<int32_t*>(base + L[k].valsA);
-            int32_t* vB = reinterpret_cast<int32_t*>(base + L[k].valsB);
-            if (p <= 0) {
-              s.in_keys = (key_kind == 2) ? (const void*)ex->keys32 : (const void*)f.ids;
-              s.in_vals = f.offsets ? reinterpret_cast<int32_t*>(base + L[k].bagmap) : nullptr;
-              // the requester-side sort carries POSITIONS (the inverse map needs them);
-              // bags are looked up from positions afterwards
-              if (ex && ex->inv != nullptr) s.in_vals = nullptr;
-              s.out_keys = kA;
-              s.out_vals = vA;
-            } else {
-              const bool a2b = (p & 1) == 1;  // pass 1: A->B, pass 2: B->A, ...
-              s.in_keys = a2b ? kA : kB;
-              s.in_vals = a2b ? vA : vB;
-              s.out_keys = a2b ? kB : kA;
-              s.out_vals = a2b ? vB : vA;
-            }
-            s.out_inv = nullptr;
-            s.out_sizes = nullptr;
-            s.n = (int32_t)f.nnz;
-            s.n_dev = ex ? ex->n_dev : nullptr;
-            s.tile_begin = tiles;
-            s.shift = (p < 0 ? 0 : p) * kRadixBits;
-            s.key_limit = (uint32_t)f.rows;
-            s.hist_slot = k;
-            s.passes = passes[k];
-            s.lbits = ex ? ex->lbits : 0;
-            tiles += bucket_tiles(f.nnz);
-          }
-          if (bp.nsegs == 0) break;
-          bp.hist = sc.hist;
-          bp.status = sc.status[p < 0 ? 0 : p];
-          bp.ticket = sc.ticket[p < 0 ? 0 : p];
-          bp.nbins = kRadixBins;
-          bp.total_tiles = tiles;
-          bp.npass = max_passes;
-          bp.pass = p < 0 ? 0 : p;
-          bp.digit_bits = kRadixBits;
-          bp.p = (key_kind == 1) ? (int32_t)feats[0].id_div : 1;
-          bp.m = 1; bp.pow2_mask = 0;
-          bp.div = feats[0].id_div;
-          bp.div_shift = ((bp.div & (bp.div - 1)) == 0 && bp.div <= (1 << 30)) ? ilog2c(bp.div) : -1;
-          if (p > 0) rc = bucket_pass_launch<RadixNextTraits>(bp, stream, HB_K_SORT_PASS);
-          else if (key_kind == 1)
-            rc = p < 0 ? bucket_hist_launch<RadixCompositeTraits>(bp, stream, HB_K_SORT_HIST)
-                       : bucket_pass_launch<RadixCompositeTraits>(bp, stream, HB_K_SORT_PASS);
-          else if (key_kind == 2)
-            rc = p < 0 ? bucket_hist_launch<RadixDirectTraits>(bp, stream, HB_K_SORT_HIST)
-                       : bucket_pass_launch<RadixDirectTraits>(bp, stream, HB_K_SORT_PASS);
-          else
-            rc = p < 0 ? bucket_hist_launch<RadixFirstTraits>(bp, stream, HB_K_SORT_HIST)
-                       : bucket_pass_launch<RadixFirstTraits>(bp, stream, HB_K_SORT_PASS);
-          if (rc != HB_OK) return rc;
-        }
-      }
-
-      // 3. runs
-      RunParams R;
-      R.status = reinterpret_cast<uint32_t*>(base + S.run_status);
-      R.ticket = reinterpret_cast<uint32_t*>(base + S.run_ticket);
-      R.d_status = d_status;
-      R.nfeats = nc;
-      size_t static_tiles = 0;
+      // 2. stable LSD radix sort (9-bit digits) + run detection: one cluster per feature
+      //    (cluster_sort.cuh); it also zeroes the hot-row queue counters of the apply
+      CsParams C;
+      C.d_status = d_status;
+      C.zero = reinterpret_cast<int32_t*>(base + S.zero_sort);
+      C.zero_words = (int32_t)(S.zero_sort_bytes / 4);
+      C.nfeats = nc;
+      C.key_kind = key_kind;
+      C.p = (key_kind == 1) ? (int32_t)feats[0].id_div : 1;
+      C.div = feats[0].id_div;
+      C.div_shift = ((C.div & (C.div - 1)) == 0 && C.div <= (1 << 30)) ? ilog2c(C.div) : -1;
       for (int k = 0; k < nc; ++k) {
         const hbUpdateFeature& f = feats[c0 + k];
         const UpdExtra* ex = extras ? &extras[c0 + k] : nullptr;
-        const bool inA = (passes[k] & 1) == 1;  // 1 pass -> A, 2 -> B, 3 -> A, ...
-        RunFeat& F = R.f[k];
-        F.keys = reinterpret_cast<uint32_t*>(base + (inA ? L[k].keysA : L[k].keysB));
-        F.vals = reinterpret_cast<int32_t*>(base + (inA ? L[k].valsA : L[k].valsB));
+        CsFeat& F = C.f[k];
+        F.in_keys = (key_kind == 2) ? (const void*)ex->keys32 : (const void*)f.ids;
+        F.in_vals = f.offsets ? reinterpret_cast<int32_t*>(base + L[k].bagmap) : nullptr;
+        // the requester-side sort carries POSITIONS (the inverse map needs them);
+        // bags are looked up from positions afterwards
+        if (ex && ex->inv != nullptr) F.in_vals = nullptr;
+        F.keys[0] = reinterpret_cast<uint32_t*>(base + L[k].keysA);
+        F.keys[1] = reinterpret_cast<uint32_t*>(base + L[k].keysB);
+        F.vals[0] = reinterpret_cast<int32_t*>(base + L[k].valsA);
+        F.vals[1] = reinterpret_cast<int32_t*>(base + L[k].valsB);
+        F.hist = reinterpret_cast<uint32_t*>(base + L[k].cs_hist);
+        F.tile_uniq = reinterpret_cast<int32_t*>(base + L[k].cs_uniq);
         F.ukey = reinterpret_cast<uint32_t*>(base + L[k].ukey);
         F.ustart = reinterpret_cast<int32_t*>(base + L[k].ustart);
         F.ubag4 = reinterpret_cast<int4*>(base + L[k].ubag4);
@@ -1183,16 +988,25 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
         F.owner_start1 = ex ? ex->owner_start1 : nullptr;
         F.n_dev = ex ? ex->n_dev : nullptr;
         F.n = (int32_t)f.nnz;
+        F.passes = passes[k];
         F.lbits = ex ? ex->lbits : 0;
-        static_tiles += run_tiles_of(f.nnz);
+        F.key_limit = (uint32_t)f.rows;
       }
-      const int maxg = device_sm_count() * 4;
-      const int grid = static_tiles < (size_t)maxg ? (int)static_tiles : maxg;
-      {
-        KernelScope ks(HB_K_RUNS, stream);
-        runs_kernel<<<grid, kUpdThreads, 0, stream>>>(R);
-        HB_CUDA_OK(cudaGetLastError());
+      {  // launch order: features with the most passes (and entries) first
+        int idx[kCsMaxFeats];
+        for (int k = 0; k < nc; ++k) idx[k] = k;
+        std::stable_sort(idx, idx + nc, [&](int a, int b) {
+          const int64_t wa = (int64_t)C.f[a].passes * cs_tiles(C.f[a].n), wb = (int64_t)C.f[b].passes * cs_tiles(C.f[b].n);
+          return wa > wb;
+        });
+        for (int k = 0; k < nc; ++k) C.order[k] = (uint8_t)idx[k];
       }
+      (void)max_passes;
+      C.timing = cs_timing_buffer();
+      if (key_kind == 1) rc = cluster_sort_launch<1>(C, stream, HB_K_SORT_PASS);
+      else if (key_kind == 2) rc = cluster_sort_launch<2>(C, stream, HB_K_SORT_PASS);
+      else rc = cluster_sort_launch<0>(C, stream, HB_K_SORT_PASS);
+      if (rc != HB_OK) return rc;
     }
 
     // 4. fused duplicate-sum + sink: the short kernels of every vector class (they also
@@ -1262,6 +1076,12 @@ int sparse_update_run(int n, const hbUpdateFeature* feats, const hbOptimizer* op
 }  // namespace hb
 
 extern "C" {
+
+// debug only (not in the public header): copies the 64 stamps of the last sort to the host
+int hbDebugSortTiming(unsigned long long* h_out) {
+  if (hb::g_cs_timing == nullptr) return HB_ERR_INVALID;
+  return cudaMemcpy(h_out, hb::g_cs_timing, 64 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
 
 int hbGroupSparseUpdateWorkspaceBytes(int n, const hbUpdateFeature* feats, size_t* bytes) {
   using namespace hb;

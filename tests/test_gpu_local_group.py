@@ -118,6 +118,10 @@ def test_sharded_200_features_c4_regime(hb, oracle):
   run_ranks(rank_cases.sharded_many_features, 8, hb, oracle)
 
 
+def test_sharded_hot_keys_lazy_adam_c5_regime(hb, oracle):
+  run_ranks(rank_cases.sharded_hot_keys_lazy_adam, 8, hb, oracle)
+
+
 @pytest.mark.parametrize('world', [2, 8])
 def test_sharded_overflow_is_reported_on_every_rank(hb, oracle, world):
   run_ranks(rank_cases.sharded_overflow, world, hb, oracle)

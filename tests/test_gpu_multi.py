@@ -117,6 +117,7 @@ def test_sharded_plan_recreate_2gpu():
   _spawn('sharded_plan_recreate')
 
 
-@pytest.mark.parametrize('case', ['sharded_lookup', 'sharded_lookup_dim64_hot'])
+@pytest.mark.parametrize('case', ['sharded_lookup', 'sharded_lookup_dim64_hot', 'sharded_many_features',
+                                  'sharded_hot_keys_lazy_adam'])
 def test_sharded_group_lookup_8gpu(case):
   _spawn(case, world=8)

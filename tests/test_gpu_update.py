@@ -171,7 +171,7 @@ def test_c2_config_as_benched(hb, oracle):
   offsets = np.arange(B + 1, dtype=np.int64)
   tol = [None] * 26
   for step in range(2):
-    ids = [bench.gen_ids_numpy(rng, B, n, 'zipf', 1.05) for n in sizes]
+    ids = [bench.gen_ids_numpy(rng, B, n, "zipf", 1.05, salt=k) for k, n in enumerate(sizes)]
     grad = (rng.randn(B, 26 * D) * 1e-2).astype(np.float32)
     out = gl.forward([torch.from_numpy(i).cuda() for i in ids]).cpu().numpy()
     gl.backward_update(torch.from_numpy(grad).cuda(), opt, check=True)
