@@ -16,6 +16,7 @@ memory and the pooled output copied back to the host inside the timed region,
 through the C-ABI host entry (hbGroupLookupForwardHost).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -50,6 +51,7 @@ def parse_args():
   p.add_argument('--cpu-sample-steps', type=int, default=3)
   p.add_argument('--no-cpu-baseline', action='store_true')
   p.add_argument('--no-e2e', action='store_true')
+  p.add_argument('--no-uniform', action='store_true')
   p.add_argument('--capacity-factor', type=float, default=0.0, help='0: world size (always safe)')
   return p.parse_args()
 
@@ -247,7 +249,7 @@ def run_reference(args):
       'unit': 'pooled-embedding-rows/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
       'ms_per_step': info['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': workload_config(args, dim, sizes),
+      'config': dict(workload_config(args, dim, sizes), reference_steps_cap=5, reference_warmup_cap=2),
       'cpu_baseline': info,
       'e2e': {'value': value, 'unit': 'pooled-embedding-rows/s', 'h2d_bytes_per_step': 0,
               'd2h_bytes_per_step': 0},
@@ -317,18 +319,29 @@ def run_ours(args):
   d_batches = [hb_.to(dev) for hb_ in h_batches]
   grad = torch.randn(B, F * dim, device=dev, generator=g)
   out = torch.empty(B, F * dim, device=dev)
-  h_out = torch.empty(B, F * dim).pin_memory()
-  d_stage = torch.empty(F, B, dtype=torch.int64, device=dev)
-  uniq_rows = [sum(int(torch.unique(db[k]).numel()) for db in d_batches) / NUM_BATCHES for k in range(F)]
+  # end-to-end leg: two (device out, pinned host out, id staging) sets, so the D2H of step t
+  # (on a copy stream) overlaps the backward of step t and the H2D + forward of step t+1
+  outs = [out, torch.empty(B, F * dim, device=dev)]
+  h_outs = [torch.empty(B, F * dim).pin_memory() for _ in range(2)]
+  d_stages = [torch.empty(F, B, dtype=torch.int64, device=dev) for _ in range(2)]
+  d2h = torch.cuda.Stream(device=dev)
+  h_metric = torch.zeros(1, dtype=torch.int32).pin_memory()
 
   def step(i, host=False):
-    if host:
-      gl.forward_host(h_batches[i % NUM_BATCHES], d_stage, out, h_out)
+    if host == 'device_out':
+      # ids from pinned host memory, pooled output stays on the device (its consumer is the
+      # on-device MLP); the step's D2H is the 4-byte status word
+      d_stages[i & 1].copy_(h_batches[i % NUM_BATCHES], non_blocking=True)
+      gl.forward([d_stages[i & 1][k] for k in range(F)], out=outs[i & 1])
+    elif host:
+      gl.forward_host(h_batches[i % NUM_BATCHES], d_stages[i & 1], outs[i & 1], h_outs[i & 1], d2h_stream=d2h)
     else:
       db = d_batches[i % NUM_BATCHES]
       gl.forward([db[k] for k in range(F)], out=out)
     if args.mode == 'train':
       gl.backward_update(grad, opt)
+    if host == 'device_out':
+      h_metric.copy_(hb._util.status_word(dev), non_blocking=True)
 
   def timed(steps, host=False):
     if world > 1:
@@ -389,7 +402,6 @@ def run_ours(args):
   L.hbProfileEnable(0)
   gl.overlap_backward_sort = True
   kern = {}
-  import ctypes as C
   for kid in range(1, 32):
     tms, n = C.c_double(0), C.c_int64(0)
     L.hbProfileGet(kid, C.byref(tms), C.byref(n))
@@ -408,69 +420,146 @@ def run_ours(args):
   shard_feats = [k for k in range(F) if k in gl.sharded_idx]
   alg = {}
   bound = {}
-  # forward gather+pool: per pooled row L*(8+4D) read + 4D written, L=1
-  alg['lookup_fwd'] = len(local_feats) * B * (8 + 4 * dim + 4 * dim)
-  # update: per id 8 B (sorted row+bag) + 4D grad; per unique row 4*4D (w, acc read+write)
+  extra = {}
+  kShortMax = 16  # csrc/sparse_update.cu: longer runs go to the hot-row kernel
+
+  def run_stats(idsets):
+    """entries / unique rows of the short-run and of the hot-row kernel, mean per batch"""
+    se = su = le = lu = 0.0
+    for ids in idsets:
+      _, c = np.unique(ids, return_counts=True)
+      lg = c > kShortMax
+      se += c[~lg].sum(); su += (~lg).sum(); le += c[lg].sum(); lu += lg.sum()
+    m = float(len(idsets))
+    return se / m, su / m, le / m, lu / m
+
   if world == 1:
-    alg['sparse_update'] = sum(B * (8 + 4 * dim) + uniq_rows[k] * 16 * dim for k in local_feats)
+    hb_np = [hb_.numpy() for hb_ in h_batches]
+    # forward gather+pool: per pooled row L*(8+4D) read + 4D written (SURVEY 8d), L=1
+    alg['lookup_fwd'] = F * B * (8 + 4 * dim + 4 * dim)
+    se = su = le = lu = 0.0
+    npass = 0.0
+    for k in range(F):
+      a_, b_, c_, d_ = run_stats([blk[k] for blk in hb_np])
+      se += a_; su += b_; le += c_; lu += d_
+      npass += 1 if sizes[k] + 2 <= 512 else (2 if sizes[k] + 2 <= (1 << 18) else (3 if sizes[k] + 2 <= (1 << 27) else 4))
+    # short-run kernel: per entry 4 B (bag) + 4D (gradient row); per unique row 24 B of run
+    # arrays + 16D (table + accumulator, read + write)
+    alg['sparse_update'] = se * (4 + 4 * dim) + su * (24 + 16 * dim)
+    alg['sparse_update_long'] = le * (4 + 4 * dim) + lu * (28 + 16 * dim)
+    # sort + runs: 8 B id in, then (key, value) 8 B out + 8 B in per pass, runs 8 B in + 28 B per unique
+    alg['sort_pass'] = B * (npass * 16 + F * 8) + (su + lu) * 28
+    extra['unique_rows_per_step'] = su + lu
+    extra['hot_row_entries_per_step'] = le
+    step_alg = alg['lookup_fwd'] + (alg['sparse_update'] + alg['sparse_update_long'] + alg['sort_pass'] if args.mode == 'train' else 0)
   else:
-    # owner side: every rank's ids with id % W == rank arrive here; regenerate the
-    # other ranks' batches (same seeds) to count entries and unique rows exactly
-    recv = {k: 0.0 for k in shard_feats}
-    uniq = {k: 0.0 for k in shard_feats}
+    # regenerate every rank's batches (same seeds): unique ids per (requester, owner)
     gens = [np.random.RandomState(1234 + r) for r in range(world)]
+    recv_u = np.zeros(world)          # unique rows asked of owner r (sum over requesters, features)
+    sent_u = 0.0                      # unique rows this rank asks for
     for _ in range(NUM_BATCHES):
       blks = [np.stack([gen_ids_numpy(gr, B, n, args.dist, args.alpha, salt=k) for k, n in enumerate(sizes)]) for gr in gens]
       for k in shard_feats:
-        mine = np.concatenate([blk[k][blk[k] % world == rank] for blk in blks])
-        recv[k] += len(mine) / NUM_BATCHES
-        uniq[k] += len(np.unique(mine)) / NUM_BATCHES
-    nrecv = sum(recv.values())
-    alg['sparse_update'] = sum(recv[k] * (8 + 4 * dim) + uniq[k] * 16 * dim for k in shard_feats)
-    # NVLink-bound kernels: bytes that must cross NVLink per launch (one direction)
-    alg['sharded_owner_gather'] = nrecv * 4 * dim * (world - 1) / world
-    alg['sharded_push_grads'] = len(shard_feats) * B * 4 * dim * (world - 1) / world
-    bound['sharded_owner_gather'] = bound['sharded_push_grads'] = 'nvlink'
-    # stitch/pool: 4 B index + 4D row read + 4D written per pooled row (L=1)
-    alg['sharded_stitch_pool'] = len(shard_feats) * B * (4 + 8 * dim)
+        for q, blk in enumerate(blks):
+          u = np.unique(blk[k])
+          cnt = np.bincount(u % world, minlength=world)
+          recv_u += cnt / NUM_BATCHES
+          if q == rank:
+            sent_u += len(u) / NUM_BATCHES
+    nsh = len(shard_feats)
+    # NVLink-bound: unique rows stored into the requesters' windows, (W-1)/W of them remote
+    alg['sharded_owner_gather'] = recv_u[rank] * 4 * dim * (world - 1) / world
+    bound['sharded_owner_gather'] = 'nvlink'
+    # stitch/pool: 4 B inverse index + 4D row read (window, mostly L2) + 4D written per pooled row
+    alg['sharded_stitch_pool'] = nsh * B * (4 + 8 * dim)
+    extra['owner_load_unique_rows'] = {'max': float(recv_u.max()), 'mean': float(recv_u.mean()),
+                                       'max_over_mean': float(recv_u.max() / max(recv_u.mean(), 1.0))}
+    extra['dedup'] = {'ids_per_rank_per_step': nsh * B, 'unique_ids_sent_per_rank_per_step': sent_u,
+                      'wire_reduction': nsh * B / max(sent_u, 1.0)}
+    # one direction, per rank and step: unique ids out (4 B) + unique rows in + unique gradient sums out
+    nv = sent_u * (world - 1) / world * (4 + 4 * dim)
+    extra['nvlink_bytes_per_step_per_rank_one_direction'] = nv
+    step_alg = None
   NVLINK_PEAK = 770.0  # GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)
   traffic = {}
   try:
     traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
   except (OSError, ValueError):
     pass
-  roofs = []
-  for name, a in alg.items():
-    if name in kern and a > 0:
-      ach = a / (kern[name]['ms_avg'] * 1e-3) / 1e9
-      bd = bound.get(name, 'hbm')
-      pk = peak if bd == 'hbm' else NVLINK_PEAK
-      roofs.append({'kernel': name, 'bound': bd, 'achieved': ach, 'peak': pk, 'unit': 'GB/s',
-                    'frac': ach / pk, 'traffic': traffic.get(name) if world == 1 else None,
-                    'alg_bytes_per_launch': a, 'ms_avg': kern[name]['ms_avg'],
-                    'peak_source': peak_src if bd == 'hbm' else
-                    'measured peer copy 770 GB/s/direction (B200_PROFILING.md); kernel time includes the wait for the peers'})
-  roofs.sort(key=lambda r: -r['ms_avg'])
+
+  def roofs_of(kern_):
+    r_ = []
+    for name, a in alg.items():
+      if name in kern_ and a > 0:
+        ach = a / (kern_[name]['ms_avg'] * 1e-3) / 1e9
+        bd = bound.get(name, 'hbm')
+        pk = peak if bd == 'hbm' else NVLINK_PEAK
+        tr = traffic.get(name) if world == 1 and args.dist == 'zipf' and dim == 32 else None
+        r_.append({'kernel': name, 'bound': bd, 'achieved': ach, 'peak': pk, 'unit': 'GB/s',
+                   'frac': ach / pk, 'traffic': tr,
+                   'traffic_source': 'profiles/traffic.json (ncu --set full, dram bytes read + written per launch, round 2)' if tr else None,
+                   'alg_bytes_per_launch': a, 'ms_avg': kern_[name]['ms_avg'],
+                   'peak_source': peak_src if bd == 'hbm' else
+                   'measured peer copy 770 GB/s/direction (B200_PROFILING.md); kernel time includes the wait for the peers'})
+    r_.sort(key=lambda r: -r['ms_avg'])
+    return r_
+  roofs = roofs_of(kern)
   roofline = roofs[0] if roofs else None
+
+  # ---- second data point: uniform ids (no hot rows, no L2 help from duplicates) ----
+  if world == 1 and args.dist == 'zipf' and not args.no_uniform:
+    saved = d_batches
+    rngu = np.random.RandomState(4321)
+    d_batches = [torch.from_numpy(np.stack([gen_ids_numpy(rngu, B, n, 'uniform', 0.0) for n in sizes])).to(dev)
+                 for _ in range(NUM_BATCHES)]
+    for i in range(3):
+      step(i)
+    ms_u = timed(K)
+    gl.overlap_backward_sort = False
+    L.hbProfileReset(); L.hbProfileEnable(1)
+    timed(K)
+    L.hbProfileEnable(0)
+    gl.overlap_backward_sort = True
+    kern_u = {}
+    for kid in range(1, 32):
+      tms, n_ = C.c_double(0), C.c_int64(0)
+      L.hbProfileGet(kid, C.byref(tms), C.byref(n_))
+      if n_.value:
+        kern_u[L.hbKernelName(kid).decode()] = {'ms_avg': tms.value / n_.value}
+    L.hbProfileReset()
+    fwd_u = kern_u.get('lookup_fwd', {}).get('ms_avg')
+    extra['uniform'] = {'ms_per_step': ms_u / K, 'value': B * F * K / (ms_u * 1e-3),
+                        'lookup_fwd_ms': fwd_u,
+                        'lookup_fwd_roofline': ({'achieved': alg['lookup_fwd'] / (fwd_u * 1e-3) / 1e9, 'peak': peak,
+                                                 'frac': alg['lookup_fwd'] / (fwd_u * 1e-3) / 1e9 / peak,
+                                                 'note': 'uniform ids over the full vocabularies: rows of the 8 large tables come from DRAM; '
+                                                         'a pure random 128-B row read sustains 4.3 TB/s on this GPU (tools/gather_peak.cu)'}
+                                                if fwd_u else None),
+                        'kernels_ms': {k_: v_['ms_avg'] for k_, v_ in kern_u.items()}}
+    d_batches = saved
 
   # ---- end-to-end through the host-buffer C-ABI entry ------------------------------
   e2e = None
-  if not args.no_e2e and world == 1:
-    for i in range(2):
+  e2e_variants = {}
+  if not args.no_e2e:
+    for i in range(3):
       step(i, host=True)
     ms_e = timed(K, host=True)
     e2e = {'value': B * F * world * K / (ms_e * 1e-3), 'unit': 'pooled-embedding-rows/s',
            'h2d_bytes_per_step': F * B * 8, 'd2h_bytes_per_step': B * F * dim * 4,
            'ms_per_step': ms_e / K,
-           'note': 'ids from pinned host memory, pooled [B, F*D] output copied back to pinned host; '
-                   'upstream gradient stays on the device (it comes from the dense MLP)'}
-  elif not args.no_e2e:
-    for i in range(2):
-      step(i, host=True)
-    ms_e = timed(K, host=True)
-    e2e = {'value': B * F * world * K / (ms_e * 1e-3), 'unit': 'pooled-embedding-rows/s',
-           'h2d_bytes_per_step': F * B * 8, 'd2h_bytes_per_step': B * F * dim * 4,
-           'ms_per_step': ms_e / K}
+           'note': 'ids from pinned host memory (hbGroupLookupForwardHost), pooled [B, F*D] output copied back to '
+                   'pinned host on a copy stream overlapping the backward and the next step (PCIe-bound: '
+                   '%.0f MB D2H per step); upstream gradient stays on the device (it comes from the dense MLP)'
+                   % (B * F * dim * 4 / 1e6)}
+    for i in range(3):
+      step(i, host='device_out')
+    ms_d = timed(K, host='device_out')
+    e2e_variants['device_out'] = {
+        'value': B * F * world * K / (ms_d * 1e-3), 'unit': 'pooled-embedding-rows/s',
+        'h2d_bytes_per_step': F * B * 8, 'd2h_bytes_per_step': 4, 'ms_per_step': ms_d / K,
+        'note': 'same, but the pooled output stays in HBM for the on-device MLP (what the reference graph '
+                'does: the op output is a GPU tensor); D2H = the 4-byte status word'}
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -482,12 +571,15 @@ def run_ours(args):
         'n_gpus': world, 'steps': K, 'warmup': W_, 'ms_per_step': ms / K, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, dim, sizes), 'clocks': clk, 'e2e': e2e,
+        'e2e_variants': e2e_variants,
         'gpu_launches': int(launches), 'host_enqueue_ms_per_step': host_ms, 'roofline': roofline, 'roofline_all': roofs,
-        'kernels': kern, 'cpu_baseline': cpu,
+        'kernels': kern, 'cpu_baseline': cpu, 'extra': extra,
         'roofline_note': 'per-kernel CUDA events recorded by the library on the launching stream in '
                          'a second pass of the same K steps (hbProfileEnable), single stream (no fwd/sort overlap)',
-        'hbm_roofline_rows_per_s_per_gpu': peak * 1e9 / (8 + 8 * dim) if args.mode == 'fwd' else
-                                           peak * 1e9 / ((8 + 8 * dim) + (8 + 20 * dim)),
+        'hbm_roofline_rows_per_s_per_gpu': (peak * 1e9 / (step_alg / (B * F)) if step_alg else None),
+        'hbm_roofline_note': ('B*F pooled rows / (algorithmic bytes of one step on THIS workload -- duplicates read once per '
+                              'entry, table rows once per unique row -- / measured HBM peak); whole step achieves %.2f of it'
+                              % (step_alg / (ms / K * 1e-3) / 1e9 / peak)) if step_alg else None,
     }
     print(json.dumps(line))
   if world > 1:

@@ -118,6 +118,7 @@ class GroupLookup:
     # descriptor cache: building ~80 ctypes structs per step costs more host time than
     # the kernels take on the device, so struct arrays are kept per set of buffers
     self._cache = {}
+    self._d2h_events = {}
     self._ev_ready = None
     world = collective.world_size if collective is not None else 1
     self.sharded_idx = [k for k, t in enumerate(self.tables)
@@ -252,11 +253,16 @@ class GroupLookup:
     self._ev_sorted.record(self._side)
     self._sort_done = self._ev_sorted
 
-  def forward_host(self, h_ids, d_stage, out, h_out, check=False):
+  def forward_host(self, h_ids, d_stage, out, h_out, check=False, d2h_stream=None):
     """Host-buffer forward (one id per bag): h_ids pinned int64 [n, B] is copied
     H2D into d_stage [n, B], the fused lookup runs, and `out` [B, sum(dim)]
     (contiguous, device) is copied D2H into pinned h_out -- all enqueued on the
-    current stream by ONE C-ABI call (hbGroupLookupForwardHost)."""
+    current stream by ONE C-ABI call (hbGroupLookupForwardHost).
+
+    d2h_stream: copy the output back on that stream instead (behind an event), so the
+    backward of this step and the H2D + forward of the next overlap the D2H; the caller
+    rotates (out, h_out) pairs, and the next forward into the same `out` waits for its
+    copy.  h_out is valid once d2h_stream (or the device) is synchronised."""
     if not (h_ids.is_pinned() and h_out.is_pinned()):
       raise ValueError('forward_host needs pinned host tensors')
     if h_ids.dtype != torch.int64 or h_ids.dim() != 2 or h_ids.shape[0] != self.n:
@@ -273,22 +279,39 @@ class GroupLookup:
     ids = [d_stage[k] for k in range(self.n)]
     with torch.cuda.device(self.device):
       self._sort_done = None
+      main = torch.cuda.current_stream()
+      pending = self._d2h_events.pop(out.data_ptr(), None)
+      if pending is not None:
+        main.wait_event(pending)   # the previous copy out of this buffer
       if self._sharded is None:
-        feats = (_lib.hbLookupFeature * self.n)()
-        for k in range(self.n):
-          feats[k] = _feature_struct(_weight_of(self.tables[k]), ids[k], None, B,
-                                     out[:, self.col_offsets[k]:], out.stride(0),
-                                     self.combiners[k])
+        def build():
+          feats = (_lib.hbLookupFeature * self.n)()
+          for k in range(self.n):
+            feats[k] = _feature_struct(_weight_of(self.tables[k]), ids[k], None, B,
+                                       out[:, self.col_offsets[k]:], out.stride(0),
+                                       self.combiners[k])
+          return feats
+        feats = self._memo('fwd_host', (d_stage.data_ptr(), out.data_ptr(), B), build)
         _lib.check(L.hbGroupLookupForwardHost(
             self.n, feats, _lib.C.c_void_p(h_ids.data_ptr()), _lib.C.c_void_p(d_stage.data_ptr()),
             _lib.C.c_size_t(h_ids.numel() * 8), _lib.C.c_void_p(out.data_ptr()),
-            _lib.C.c_void_p(h_out.data_ptr()), _lib.C.c_size_t(out.numel() * 4),
+            _lib.C.c_void_p(h_out.data_ptr()), _lib.C.c_size_t(out.numel() * 4 if d2h_stream is None else 0),
             _lib.C.c_void_p(st.data_ptr()), _util.stream_ptr()), 'GroupLookup.forward_host')
-        self._saved = (ids, [None] * self.n, B, None)
+        self._saved = (ids, [None] * self.n, B, ('host', d_stage.data_ptr(), B))
       else:
         d_stage.copy_(h_ids, non_blocking=True)
         self.forward(ids, out=out)
-        h_out.copy_(out, non_blocking=True)
+        if d2h_stream is None:
+          h_out.copy_(out, non_blocking=True)
+      if d2h_stream is not None:
+        ready = torch.cuda.Event()
+        ready.record(main)
+        d2h_stream.wait_event(ready)
+        with torch.cuda.stream(d2h_stream):
+          h_out.copy_(out, non_blocking=True)
+          done = torch.cuda.Event()
+          done.record(d2h_stream)
+        self._d2h_events[out.data_ptr()] = done
     if check:
       _util.check_status(self.device)
     return h_out
