@@ -107,7 +107,7 @@ SYMBOLS = [
     'hbPartitionWorkspaceBytes', 'hbPartitionByModuloN', 'hbPartitionByDualModuloN',
     'hbGroupLookupForward', 'hbGroupSparseUpdateWorkspaceBytes',
     'hbGroupLookupBackwardUpdate', 'hbGroupSparseSort', 'hbGroupSparseApply', 'hbCastN', 'hbCacheLookup',
-    'hbCommCreate', 'hbCommConnect', 'hbCommCreateLocalGroup', 'hbCommSetStatusWord',
+    'hbCommCreate', 'hbCommConnect', 'hbGetUniqueId', 'hbCommCreateFromId', 'hbCommCreateLocalGroup', 'hbCommSetStatusWord',
     'hbAllreduceSumF32', 'hbCommDestroy', 'hbCommRank', 'hbCommWorldSize',
     'hbCommWindow', 'hbCommWindowBytes', 'hbCommBarrier',
     'hbAlltoallvNSizes', 'hbAlltoallvN',

@@ -25,6 +25,8 @@
 // trailing barrier unnecessary (see DESIGN.md "window reuse").
 #include <stdlib.h>
 #include <string.h>
+#include <errno.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <chrono>
@@ -734,3 +736,108 @@ int hbAllreduceSumF32(hbComm* c, const float* d_in, float* d_out, int64_t count,
 }
 
 }  // extern "C"
+
+// ---- bootstrap by a broadcast 128-byte id (the reference's protocol) -----------------------
+// The reference creates its communicator from ONE 128-byte id that rank 0 generates
+// (HbGetNcclId, nccl_get_id.cc:35-70) and the Python side broadcasts
+// (distribute/collective.py:108-115); HbCreateNcclCollective(handle, id) then runs on every
+// rank (nccl_create.cc:45-62).  Our tokens are per rank (an IPC handle each), so the id
+// names a rendezvous directory on the node (one NVSwitch domain = one node): every rank
+// writes its token file there and reads the others'.
+static std::string rendezvous_dir(const unsigned char* id) {
+  const char* root = getenv("HB_B200_RENDEZVOUS_DIR");
+  std::string d = (root != nullptr && root[0]) ? root : "/dev/shm";
+  char tag[40];
+  uint64_t a, b;
+  memcpy(&a, id + 8, 8);
+  memcpy(&b, id + 16, 8);
+  snprintf(tag, sizeof(tag), "/hb_b200_%016llx%016llx", (unsigned long long)a, (unsigned long long)b);
+  return d + tag;
+}
+
+extern "C" int hbGetUniqueId(unsigned char id_out[HB_COMM_TOKEN_BYTES]) {
+  using namespace hb;
+  HB_REQUIRE(id_out, "hbGetUniqueId: null argument");
+  memset(id_out, 0, HB_COMM_TOKEN_BYTES);
+  const uint32_t magic = kTokenMagic ^ 0x1d1d1d1du;
+  memcpy(id_out, &magic, 4);
+  uint64_t r[2] = {0, 0};
+  FILE* f = fopen("/dev/urandom", "rb");
+  if (f != nullptr) {
+    if (fread(r, 1, sizeof(r), f) != sizeof(r)) r[0] = 0;
+    fclose(f);
+  }
+  if (r[0] == 0) {
+    r[0] = (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count();
+    r[1] = ((uint64_t)getpid() << 32) ^ (uint64_t)(uintptr_t)id_out;
+  }
+  memcpy(id_out + 8, r, 16);
+  return HB_OK;
+}
+
+extern "C" int hbCommCreateFromId(const unsigned char id[HB_COMM_TOKEN_BYTES], int rank, int world_size,
+                                  int local_size, size_t window_bytes, hbComm** comm) {
+  using namespace hb;
+  HB_REQUIRE(id && comm, "hbCommCreateFromId: null argument");
+  uint32_t magic;
+  memcpy(&magic, id, 4);
+  HB_REQUIRE(magic == (kTokenMagic ^ 0x1d1d1d1du), "hbCommCreateFromId: not an id made by hbGetUniqueId");
+  unsigned char token[HB_COMM_TOKEN_BYTES];
+  int rc = hbCommCreate(rank, world_size, local_size, window_bytes, comm, token);
+  if (rc != HB_OK) return rc;
+  if (world_size == 1) return HB_OK;
+  const std::string dir = rendezvous_dir(id);
+  if (mkdir(dir.c_str(), 0700) != 0 && errno != EEXIST) {
+    set_last_error("hbCommCreateFromId: cannot create %s: %s", dir.c_str(), strerror(errno));
+    hbCommDestroy(*comm);
+    *comm = nullptr;
+    return HB_ERR_COMM;
+  }
+  auto path = [&](int q, const char* suffix) { return dir + "/" + std::to_string(q) + suffix; };
+  {  // write-then-rename: a reader never sees a partial token
+    const std::string tmp = path(rank, ".tmp"), fin = path(rank, ".tok");
+    FILE* f = fopen(tmp.c_str(), "wb");
+    const bool ok = f != nullptr && fwrite(token, 1, HB_COMM_TOKEN_BYTES, f) == HB_COMM_TOKEN_BYTES;
+    if (f != nullptr) fclose(f);
+    if (!ok || rename(tmp.c_str(), fin.c_str()) != 0) {
+      set_last_error("hbCommCreateFromId: cannot publish the token in %s: %s", dir.c_str(), strerror(errno));
+      hbCommDestroy(*comm);
+      *comm = nullptr;
+      return HB_ERR_COMM;
+    }
+  }
+  std::string all((size_t)world_size * HB_COMM_TOKEN_BYTES, '\0');
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int q = 0; q < world_size; ++q) {
+    while (true) {
+      FILE* f = fopen(path(q, ".tok").c_str(), "rb");
+      if (f != nullptr) {
+        const size_t got = fread(&all[(size_t)q * HB_COMM_TOKEN_BYTES], 1, HB_COMM_TOKEN_BYTES, f);
+        fclose(f);
+        if (got == HB_COMM_TOKEN_BYTES) break;
+      }
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
+        set_last_error("hbCommCreateFromId: rank %d never published its token in %s (120 s)", q, dir.c_str());
+        hbCommDestroy(*comm);
+        *comm = nullptr;
+        return HB_ERR_COMM;
+      }
+      usleep(2000);
+    }
+  }
+  rc = hbCommConnect(*comm, reinterpret_cast<const unsigned char*>(all.data()));
+  if (rc != HB_OK) {
+    hbCommDestroy(*comm);
+    *comm = nullptr;
+    return rc;
+  }
+  // every rank has mapped every window once all ".ok" files exist; the last one cleans up
+  { FILE* f = fopen(path(rank, ".ok").c_str(), "wb"); if (f != nullptr) fclose(f); }
+  bool all_ok = true;
+  for (int q = 0; q < world_size; ++q) all_ok = all_ok && access(path(q, ".ok").c_str(), F_OK) == 0;
+  if (all_ok) {
+    for (int q = 0; q < world_size; ++q) { unlink(path(q, ".tok").c_str()); unlink(path(q, ".ok").c_str()); }
+    rmdir(dir.c_str());
+  }
+  return HB_OK;
+}

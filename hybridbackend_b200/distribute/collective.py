@@ -61,7 +61,7 @@ class Collective:
   _instance = None
 
   def __init__(self, rank, world_size, local_size=None, window_bytes=64 << 20,
-               device=None, token_allgather=None, _handle=None):
+               device=None, token_allgather=None, _handle=None, unique_id=None):
     self.rank, self.world_size = int(rank), int(world_size)
     self.local_size = int(local_size or world_size)
     self.device = torch.device(device if device is not None else
@@ -71,6 +71,17 @@ class Collective:
     L = _lib.lib()
     if _handle is not None:  # member of an in-process group (local_group)
       self._comm = _handle
+      self.window_bytes = int(L.hbCommWindowBytes(self._comm))
+      return
+    if unique_id is not None:
+      # the reference's protocol (distribute/collective.py:108-115): one 128-byte id made
+      # by rank 0 (Collective.get_unique_id) and broadcast by the caller
+      if len(unique_id) != _lib.TOKEN_BYTES:
+        raise ValueError('unique_id must be the 128 bytes Collective.get_unique_id() returned')
+      buf = (C.c_ubyte * _lib.TOKEN_BYTES).from_buffer_copy(bytes(unique_id))
+      with torch.cuda.device(self.device):
+        _lib.check(L.hbCommCreateFromId(buf, self.rank, self.world_size, self.local_size,
+                                        C.c_size_t(window_bytes), C.byref(self._comm)), 'Collective(unique_id)')
       self.window_bytes = int(L.hbCommWindowBytes(self._comm))
       return
     token = (C.c_ubyte * _lib.TOKEN_BYTES)()
@@ -88,6 +99,14 @@ class Collective:
         buf = (C.c_ubyte * len(all_tokens)).from_buffer_copy(all_tokens)
         _lib.check(L.hbCommConnect(self._comm, buf), 'Collective.connect')
     self.window_bytes = int(L.hbCommWindowBytes(self._comm))
+
+  @staticmethod
+  def get_unique_id():
+    """128-byte communicator id, made on one rank and broadcast to the others (the
+    counterpart of HbGetNcclId, nccl_get_id.cc:35-70)."""
+    buf = (C.c_ubyte * _lib.TOKEN_BYTES)()
+    _lib.check(_lib.lib().hbGetUniqueId(buf), 'get_unique_id')
+    return bytes(buf)
 
   @classmethod
   def local_group(cls, world_size, window_bytes=64 << 20, device=None):

@@ -223,6 +223,16 @@ typedef struct hbComm hbComm;
 int hbCommCreate(int rank, int world_size, int local_size, size_t window_bytes,
                  hbComm** comm, unsigned char token_out[HB_COMM_TOKEN_BYTES]);
 int hbCommConnect(hbComm* comm, const unsigned char* all_tokens /* world*128 */);
+/* The reference's own bootstrap protocol: ONE 128-byte id made on rank 0 (replaces
+ * HbGetNcclId, nccl_get_id.cc:35-70: `id: int64[16]`), broadcast by the caller
+ * (distribute/collective.py:108-115), then hbCommCreateFromId on every rank (replaces
+ * HbCreateNcclCollective(handle, id; world_size, local_size, rank), nccl_create.cc:45-62).
+ * The id names a rendezvous directory on the node ($HB_B200_RENDEZVOUS_DIR, default
+ * /dev/shm) through which the ranks exchange their IPC tokens; == hbCommCreate + the
+ * out-of-band all-gather + hbCommConnect.  Blocks until all ranks arrived (120 s). */
+int hbGetUniqueId(unsigned char id_out[HB_COMM_TOKEN_BYTES]);
+int hbCommCreateFromId(const unsigned char id[HB_COMM_TOKEN_BYTES], int rank, int world_size,
+                       int local_size, size_t window_bytes, hbComm** comm);
 /* In-process group: world_size communicators on the CURRENT device whose peer
  * windows are each other's allocations (no IPC, no second GPU).  One host thread
  * per rank then drives comms[r] through the very same entry points and kernels

@@ -1,0 +1,1 @@
+#include "tensorflow/core/framework/op_kernel.h"

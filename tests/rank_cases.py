@@ -475,3 +475,24 @@ def sharded_plan_recreate(env):
     gl.close()
   coll.close()
   soft.done()
+
+
+def bootstrap_from_unique_id(env):
+  """The reference's bootstrap protocol: rank 0 makes ONE 128-byte id (HbGetNcclId), it is
+  broadcast (here over torch.distributed, in the reference over TF), every rank creates
+  its communicator from it (HbCreateNcclCollective) -- then an alltoallv runs over it."""
+  import torch.distributed as dist
+  rank, world, dev, hb = env.rank, env.world, env.device, env.hb
+  box = [hb.distribute.Collective.get_unique_id() if rank == 0 else None]
+  dist.broadcast_object_list(box, src=0)
+  coll = hb.distribute.Collective(rank, world, window_bytes=8 << 20, device=dev, unique_id=box[0])
+  sizes = torch.tensor([rank + 1 + q for q in range(world)], dtype=torch.int32, device=dev)
+  x = torch.full((int(sizes.sum()),), float(rank), device=dev)
+  out, osz = coll.alltoall(x, sizes)
+  torch.cuda.synchronize()
+  exp_sz = [q + 1 + rank for q in range(world)]
+  exp = np.concatenate([np.full(exp_sz[q], float(q), np.float32) for q in range(world)])
+  ok = np.array_equal(osz.cpu().numpy(), np.array(exp_sz, np.int32)) and np.array_equal(out.cpu().numpy(), exp)
+  env.barrier()
+  coll.close()
+  assert ok, f'rank {rank}: alltoallv over the id-bootstrapped communicator is wrong'

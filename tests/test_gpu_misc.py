@@ -80,3 +80,16 @@ def test_lookup_python_surface(hb, oracle):
   assert all(t.numel() == 0 for t in e)
   with pytest.raises(ValueError, match='1D'):
     hb.embedding.lookup(torch.zeros(2, 32, dtype=torch.int64, device='cuda'), torch.zeros(1, dtype=torch.int64, device='cuda'))
+
+
+def test_unique_id_bootstrap_world1(hb):
+  """hbGetUniqueId / hbCommCreateFromId (the reference's HbGetNcclId ->
+  HbCreateNcclCollective protocol); the multi-rank exchange is test_gpu_multi.py's."""
+  uid = hb.distribute.Collective.get_unique_id()
+  assert len(uid) == 128 and uid != hb.distribute.Collective.get_unique_id()
+  coll = hb.distribute.Collective(0, 1, window_bytes=1 << 20, unique_id=uid)
+  coll.barrier()
+  torch.cuda.synchronize()
+  coll.close()
+  with pytest.raises(RuntimeError):
+    hb.distribute.Collective(0, 1, window_bytes=1 << 20, unique_id=bytes(128))

@@ -117,6 +117,10 @@ def test_sharded_plan_recreate_2gpu():
   _spawn('sharded_plan_recreate')
 
 
+def test_bootstrap_from_unique_id_2gpu():
+  _spawn('bootstrap_from_unique_id')
+
+
 @pytest.mark.parametrize('case', ['sharded_lookup', 'sharded_lookup_dim64_hot', 'sharded_many_features',
                                   'sharded_hot_keys_lazy_adam'])
 def test_sharded_group_lookup_8gpu(case):
