@@ -162,6 +162,11 @@ cluster_sort_runs_kernel(const __grid_constant__ CsParams P) {
   }
   const int T = (n + kCsTile - 1) / kCsTile;
   const bool single = T <= kCsCluster;   // at most one tile per CTA: ranks stay in registers
+  // One tile in all (small batches, the owner side of the sharded path): rank 0 sorts it
+  // entirely in shared memory -- no ping-pong through global memory, no fences, no cluster
+  // barriers -- and the other CTAs of the cluster leave (nobody ever waits on a barrier).
+  const bool local = T <= 1;
+  if (local && crank != 0) return;
 
   int stamp_i = 0;
   auto stamp = [&]() {
@@ -194,7 +199,8 @@ cluster_sort_runs_kernel(const __grid_constant__ CsParams P) {
 #pragma unroll
       for (int j = 0; j < kCsItems; ++j) {
         const int i = wbase + j * 32 + (int)lane;
-        key[j] = (i < n) ? ldcg_u32(F.keys[(p - 1) & 1] + i) : 0xFFFFFFFFu;
+        if (local) key[j] = (i < n) ? S.keys[i] : 0xFFFFFFFFu;   // staged by the previous pass
+        else key[j] = (i < n) ? ldcg_u32(F.keys[(p - 1) & 1] + i) : 0xFFFFFFFFu;
       }
     }
     __syncthreads();
@@ -253,15 +259,16 @@ cluster_sort_runs_kernel(const __grid_constant__ CsParams P) {
       if (!single) __syncthreads();
     }
     stamp();
-    __threadfence();
+    if (!local) __threadfence();
     stamp();
-    cluster.sync();
+    if (!local) cluster.sync();
     stamp();
     // ---- phase 2: bases, staging, write-out ---------------------------------------------
     uint32_t* okeys = F.keys[p & 1];
     int32_t* ovals = F.vals[p & 1];
     for (int t = crank; t < T; t += kCsCluster) {
       int pre = 0, tot = 0;
+      if (local) __syncthreads();   // hist row written by this CTA (read back through L2)
       for (int t0 = 0; t0 < T; t0 += 8) {
         uint32_t h[8];
 #pragma unroll
@@ -295,8 +302,10 @@ cluster_sort_runs_kernel(const __grid_constant__ CsParams P) {
       for (int j = 0; j < kCsItems; ++j) {
         const int i = wbase + j * 32 + (int)lane;
         if (p == 0) val[j] = (F.in_vals != nullptr && i < n) ? F.in_vals[i] : i;
+        else if (local) val[j] = (i < n) ? S.vals[i] : 0;
         else val[j] = (i < n) ? __ldcg(F.vals[(p - 1) & 1] + i) : 0;
       }
+      if (local) __syncthreads();   // every thread holds its keys / values before the stage is rewritten
 #pragma unroll
       for (int j = 0; j < kCsItems; ++j) {
         const int i = wbase + j * 32 + (int)lane;
@@ -308,6 +317,7 @@ cluster_sort_runs_kernel(const __grid_constant__ CsParams P) {
         }
       }
       __syncthreads();
+      if (!local || p == F.passes - 1)
       for (int k = tid; k < tile_n; k += kCsThreads) {
         const uint32_t kk = S.keys[k];
         const int b = (int)((kk >> shift) & (kCsBins - 1));
@@ -318,9 +328,9 @@ cluster_sort_runs_kernel(const __grid_constant__ CsParams P) {
       __syncthreads();
     }
     stamp();
-    __threadfence();
+    if (!local) __threadfence();
     stamp();
-    cluster.sync();
+    if (!local) cluster.sync();
     stamp();
   }
 
@@ -362,8 +372,12 @@ cluster_sort_runs_kernel(const __grid_constant__ CsParams P) {
     if (tid == 0) F.tile_uniq[t] = tile_total;
   }
   stamp();
-  __threadfence();
-  cluster.sync();
+  if (!local) {
+    __threadfence();
+    cluster.sync();
+  } else {
+    __syncthreads();
+  }
   stamp();
   for (int t = crank; t < T; t += kCsCluster) {
     if (!single) excl = cs_block_excl_scan(scan_tile(t), S.scan, nullptr);
