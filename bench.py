@@ -296,9 +296,8 @@ def run_ours(args):
   # ---- tables (row-sharded where the reference shards them) ----------------------
   coll = None
   if world > 1:
-    from hybridbackend_b200.embedding.sharded import plan_window_bytes
-    sharded_dims = [dim for n in sizes if not hb.embedding.is_small_table(n, world, -1)]
-    wbytes = plan_window_bytes(world, [B] * len(sharded_dims), sharded_dims, args.capacity_factor)
+    from hybridbackend_b200.embedding.sharded import group_window_bytes
+    wbytes = group_window_bytes(world, sizes, [dim] * F, [B] * F, args.capacity_factor)
     coll = hb.distribute.Collective(rank, world, window_bytes=wbytes, device=dev)
   g = torch.Generator(device=dev).manual_seed(1234 + rank)
   tables = []

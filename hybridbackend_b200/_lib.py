@@ -30,11 +30,26 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-  """nvcc-compile every .cu for sm_100a into hybridbackend_b200/lib/ (in-tree)."""
+  """nvcc-compile every .cu for sm_100a into hybridbackend_b200/lib/ (in-tree).
+  Safe against concurrent callers (N ranks of one torchrun importing the package on a
+  fresh box): one builder at a time under a file lock, objects and the library are
+  written to temporary names and renamed into place."""
   if not force and not _stale():
     return _SO
-  nvcc = os.environ.get('NVCC', 'nvcc')
+  import fcntl  # pylint: disable=import-outside-toplevel
   os.makedirs(os.path.dirname(_SO), exist_ok=True)
+  with open(os.path.join(os.path.dirname(_SO), '.build.lock'), 'w') as lock:
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+      if not force and not _stale():   # another process built it while we waited
+        return _SO
+      return _build_locked(force, verbose)
+    finally:
+      fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
+  nvcc = os.environ.get('NVCC', 'nvcc')
   objdir = os.path.join(_PKG, 'lib', 'obj')
   os.makedirs(objdir, exist_ok=True)
   objs = []
@@ -46,16 +61,26 @@ def build(force=False, verbose=False):
     if (not force and os.path.exists(obj) and
         all(os.path.getmtime(obj) > os.path.getmtime(d) for d in [src] + hdrs)):
       continue
-    cmd = [nvcc] + NVCC_FLAGS + ['-c', src, '-o', obj]
+    tmp = obj + f'.tmp{os.getpid()}'
+    cmd = [nvcc] + NVCC_FLAGS + ['-c', src, '-o', tmp]
     if verbose:
       print(' '.join(cmd))
-    procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
-  for cmd, p in procs:
+    procs.append((cmd, tmp, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+  failed = None
+  for cmd, tmp, obj, p in procs:
     out, _ = p.communicate()
     if p.returncode != 0:
-      raise RuntimeError('nvcc failed: %s\n%s' % (' '.join(cmd), out.decode()))
-  link = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', _SO] + objs
+      failed = failed or RuntimeError('nvcc failed: %s\n%s' % (' '.join(cmd), out.decode()))
+      if os.path.exists(tmp):
+        os.remove(tmp)
+    else:
+      os.replace(tmp, obj)
+  if failed is not None:
+    raise failed
+  tmp_so = _SO + f'.tmp{os.getpid()}'
+  link = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', tmp_so] + objs
   subprocess.check_call(link)
+  os.replace(tmp_so, _SO)
   return _SO
 
 

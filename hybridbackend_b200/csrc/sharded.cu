@@ -400,6 +400,11 @@ struct hbShardedPlan {
   std::vector<hb::UpdViews> req_views;
   uint32_t epoch;          // epoch of the last forward
   bool have_forward;
+  // the owner's sort of the received rows needs only ids_in, complete once the owner gather
+  // has started: it runs on a side stream next to the stitch instead of in the backward
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  bool owner_sorted;
 };
 
 namespace hb {
@@ -455,6 +460,34 @@ static void requester_jobs(const hbShardedPlan* pl, const hbShardedFeature* feat
     e.emit_remote_base = pl->meta[k].remote_base;
     e.emit_off = pl->layout.grads_in[k];
     e.emit_cap = (int32_t)pl->layout.cap[k];
+  }
+}
+
+// the owner-side update job: rows received in ids_in / grads_in, counts on the device
+static void owner_jobs(const hbShardedPlan* pl, const hbShardedFeature* feats, std::vector<hbUpdateFeature>* of,
+                       std::vector<UpdExtra>* oe) {
+  const int n = pl->n, W = pl->comm->world;
+  of->resize(n);
+  oe->resize(n);
+  unsigned char* mywin = pl->comm->base + control_bytes();
+  for (int k = 0; k < n; ++k) {
+    hbUpdateFeature& f = (*of)[k];
+    memset(&f, 0, sizeof(hbUpdateFeature));
+    f.table = feats[k].shard;
+    f.slot0 = feats[k].slot0;
+    f.slot1 = feats[k].slot1;
+    f.rows = feats[k].shard_rows;
+    f.ids = nullptr;
+    f.offsets = nullptr;
+    f.nbags = f.nnz = pl->layout.cap[k];
+    f.grad = reinterpret_cast<const float*>(mywin + pl->layout.grads_in[k]);
+    f.grad_stride = pl->dims[k];
+    f.dim = pl->dims[k];
+    f.combiner = HB_SUM;
+    f.id_div = W;
+    (*oe)[k].key_kind = 2;
+    (*oe)[k].keys32 = reinterpret_cast<const uint32_t*>(mywin + pl->layout.ids_in[k]);
+    (*oe)[k].n_dev = &pl->meta[k].recv_clamped;
   }
 }
 
@@ -556,6 +589,17 @@ int hbShardedPlanCreate(hbComm* comm, int n, const int64_t* max_nnz, const int32
   pl->req_views.resize(n);
   pl->epoch = 0;
   pl->have_forward = false;
+  pl->owner_sorted = false;
+  pl->side = nullptr;
+  pl->ev_fork = pl->ev_join = nullptr;
+  if (cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    set_last_error("hbShardedPlanCreate: cannot create the side stream");
+    cudaFree(pl->local);
+    delete pl;
+    return HB_ERR_CUDA;
+  }
   comm->reserved_bytes = align_up(pl->layout.total, 4096);
   cudaDeviceSynchronize();
   *plan = pl;
@@ -565,6 +609,9 @@ int hbShardedPlanCreate(hbComm* comm, int n, const int64_t* max_nnz, const int32
 int hbShardedPlanDestroy(hbShardedPlan* pl) {
   if (!pl) return HB_OK;
   cudaDeviceSynchronize();
+  if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+  if (pl->ev_join) cudaEventDestroy(pl->ev_join);
+  if (pl->side) cudaStreamDestroy(pl->side);
   if (pl->local) cudaFree(pl->local);
   if (pl->comm) pl->comm->reserved_bytes = 0;
   delete pl;
@@ -640,9 +687,23 @@ int hbShardedLookupForward(hbShardedPlan* pl, const hbShardedFeature* feats, int
       return HB_OK;
     }
     if (phase == 2) {
-      KernelScope ks(HB_K_SH_OWNER_GATHER, stream);
-      sh_owner_gather_kernel<<<sms * 8, kShThreads, 0, stream>>>(P);
-      HB_CUDA_OK(cudaGetLastError());
+      {
+        KernelScope ks(HB_K_SH_OWNER_GATHER, stream);
+        sh_owner_gather_kernel<<<sms * 8, kShThreads, 0, stream>>>(P);
+        HB_CUDA_OK(cudaGetLastError());
+      }
+      // ids_in is complete behind the gather's flag wait: sort it for the backward now, on
+      // the side stream (joined by the owner apply)
+      std::vector<hbUpdateFeature> of;
+      std::vector<UpdExtra> oe;
+      owner_jobs(pl, feats, &of, &oe);
+      HB_CUDA_OK(cudaEventRecord(pl->ev_fork, stream));
+      HB_CUDA_OK(cudaStreamWaitEvent(pl->side, pl->ev_fork, 0));
+      int rc3 = sparse_update_run(n, of.data(), nullptr, pl->own_ws, pl->own_ws_bytes, d_status, pl->side, nullptr,
+                                  oe.data(), nullptr, kPhaseSort, nullptr);
+      if (rc3 != HB_OK) return rc3;
+      HB_CUDA_OK(cudaEventRecord(pl->ev_join, pl->side));
+      pl->owner_sorted = true;
       return HB_OK;
     }
     // stitch + pool from the local rows_in window through the inverse map
@@ -700,32 +761,19 @@ int hbShardedLookupBackwardUpdate(hbShardedPlan* pl, const hbShardedFeature* fea
       HB_CUDA_OK(cudaGetLastError());
       return HB_OK;
     }
-    // owner: sort the received rows, sum duplicates across ranks, apply the optimizer
-    std::vector<hbUpdateFeature> of(n);
-    std::vector<UpdExtra> oe(n);
-    unsigned char* mywin = c->base + control_bytes();
-    for (int k = 0; k < n; ++k) {
-      memset(&of[k], 0, sizeof(hbUpdateFeature));
-      of[k].table = feats[k].shard;
-      of[k].slot0 = feats[k].slot0;
-      of[k].slot1 = feats[k].slot1;
-      of[k].rows = feats[k].shard_rows;
-      of[k].ids = nullptr;
-      of[k].offsets = nullptr;
-      of[k].nbags = of[k].nnz = pl->layout.cap[k];
-      of[k].grad = reinterpret_cast<const float*>(mywin + pl->layout.grads_in[k]);
-      of[k].grad_stride = pl->dims[k];
-      of[k].dim = pl->dims[k];
-      of[k].combiner = HB_SUM;
-      of[k].id_div = W;
-      oe[k].key_kind = 2;
-      oe[k].keys32 = reinterpret_cast<const uint32_t*>(mywin + pl->layout.ids_in[k]);
-      oe[k].n_dev = &pl->meta[k].recv_clamped;
-    }
+    // owner: the received rows were sorted at forward time (side stream); sum duplicates
+    // across ranks, apply the optimizer
+    std::vector<hbUpdateFeature> of;
+    std::vector<UpdExtra> oe;
+    owner_jobs(pl, feats, &of, &oe);
+    int phases = kPhaseApply;
+    if (pl->owner_sorted) HB_CUDA_OK(cudaStreamWaitEvent(stream, pl->ev_join, 0));
+    else phases |= kPhaseSort;
+    pl->owner_sorted = false;
     Control* mine = reinterpret_cast<Control*>(c->base);
     WaitSpec w{&mine->plan_flags[3][0], pl->epoch, W};
     return sparse_update_run(n, of.data(), opt, pl->own_ws, pl->own_ws_bytes, d_status, stream, &w,
-                             oe.data(), nullptr, kPhaseSort | kPhaseApply, nullptr);
+                             oe.data(), nullptr, phases, nullptr);
   });
 }
 

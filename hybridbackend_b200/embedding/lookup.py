@@ -332,8 +332,26 @@ class GroupLookup:
     st = _util.status_word(self.device)
     L = _lib.lib()
     with torch.cuda.device(self.device):
+      rep_done = None
       if self.local_idx and self._sync():
-        self._replicated_dense_update(ids, offsets, B, grad, optimizer, desc, st)
+        # replicated small tables: densify -> all-reduce -> dense apply is a chain of a dozen
+        # tiny launches; it runs on the side stream next to the sharded backward (different
+        # tables, different window region) and is joined at the end
+        if self._side is None:
+          self._side = torch.cuda.Stream(device=self.device)
+          self._ev_ready = torch.cuda.Event()
+          self._ev_sorted = torch.cuda.Event()
+        main = torch.cuda.current_stream()
+        if self._sharded is not None:
+          fork = torch.cuda.Event()
+          fork.record(main)
+          self._side.wait_event(fork)
+          with torch.cuda.stream(self._side):
+            self._replicated_dense_update(ids, offsets, B, grad, optimizer, desc, st)
+            rep_done = torch.cuda.Event()
+            rep_done.record(self._side)
+        else:
+          self._replicated_dense_update(ids, offsets, B, grad, optimizer, desc, st)
       elif self.local_idx:
         feats, need = self._update_feats(ids, offsets, B, grad, optimizer, in_key=in_key)
         m = len(feats)
@@ -353,6 +371,8 @@ class GroupLookup:
       if self._sharded is not None:
         self._sharded.backward_update(grad, [self.col_offsets[k] for k in self.sharded_idx],
                                       optimizer, desc, st)
+      if rep_done is not None:
+        torch.cuda.current_stream().wait_event(rep_done)
     if check:
       _util.check_status(self.device)
 

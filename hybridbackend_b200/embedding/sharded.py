@@ -16,6 +16,19 @@ def plan_window_bytes(world, max_nnz, dims, capacity_factor=None):
       world, n, _lib.i64_array(max_nnz), _lib.i32_array(dims), C.c_double(cf)))
 
 
+def group_window_bytes(world, sizes, dims, max_nnz, capacity_factor=None, batch_size=-1):
+  """Window size a Collective needs to host a GroupLookup over tables of `sizes` rows:
+  the sharded plan of the tables the sharding rule shards, plus both halves of the
+  dense-gradient all-reduce of the replicated small ones (hbAllreduceSumF32 needs
+  world x count floats per half), plus 1 MB of slack for the op-surface collectives."""
+  from hybridbackend_b200.embedding.sharding import is_small_table  # pylint: disable=import-outside-toplevel
+  sh = [k for k, n in enumerate(sizes) if world > 1 and not is_small_table(n, world, batch_size)]
+  plan = plan_window_bytes(world, [max_nnz[k] for k in sh], [dims[k] for k in sh], capacity_factor) if sh else 0
+  dense = sum(sizes[k] * dims[k] for k in range(len(sizes)) if k not in sh) if world > 1 else 0
+  ar = 2 * world * ((dense * 4 + 255) // 256 * 256 + 256)
+  return int(plan + ar + (1 << 20))
+
+
 class ShardedGroup:
   """The sharded features of a GroupLookup: partition -> NVSwitch push -> owner
   gather -> stitch/pool (forward) and gradient push -> owner dedup + sparse
