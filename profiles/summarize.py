@@ -17,7 +17,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 KEY = {'hb::lookup_fwd_kernel': 'lookup_fwd', 'hb::sparse_update_kernel': 'sparse_update',
        'hb::sparse_update_fixup_kernel': 'sparse_update_fixup', 'hb::bucket_pass_kernel': 'sort_pass',
        'hb::bucket_hist_kernel': 'sort_hist', 'hb::sh_owner_gather_kernel': 'sharded_owner_gather',
-       'hb::sh_push_grads_kernel': 'sharded_push_grads'}
+       'hb::sh_push_grads_kernel': 'sharded_push_grads',
+       # round 2
+       'hb::update_short_kernel': 'sparse_update', 'hb::update_long_kernel': 'sparse_update_long',
+       'hb::cluster_sort_runs_kernel': 'sort_pass', 'update_short_kernel': 'sparse_update',
+       'update_long_kernel': 'sparse_update_long', 'cluster_sort_runs_kernel': 'sort_pass',
+       'lookup_fwd_kernel': 'lookup_fwd'}
 
 
 def launches(tag, path):
