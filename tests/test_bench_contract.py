@@ -35,8 +35,12 @@ def test_reference_arm_other_ranks_exit_quietly():
   assert out.strip() == ''
 
 
-def test_committed_bench_line_has_contract_keys():
-  d = json.load(open(os.path.join(ROOT, 'profiles', 'bench_r1_n1.json')))
+import pytest
+
+
+@pytest.mark.parametrize('name', ['bench_r1_n1.json', 'bench_r2_n1.json'])
+def test_committed_bench_line_has_contract_keys(name):
+  d = json.load(open(os.path.join(ROOT, 'profiles', name)))
   for k in BASE_KEYS + ['clocks', 'e2e', 'gpu_launches', 'roofline', 'cpu_baseline']:
     assert k in d, k
   r = d['roofline']
@@ -50,3 +54,17 @@ def test_committed_bench_line_has_contract_keys():
   cb = d['cpu_baseline']
   assert cb['kind'] in ('port', 'reference') and cb['cores'] >= 1 and cb['sample']
   assert not set(d['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+
+
+def test_round2_line_carries_the_second_data_points():
+  d = json.load(open(os.path.join(ROOT, 'profiles', 'bench_r2_n1.json')))
+  u = d['extra']['uniform']
+  assert u['ms_per_step'] > 0 and 0 < u['lookup_fwd_roofline']['frac'] < 1.5
+  v = d['e2e_variants']['device_out']
+  assert v['d2h_bytes_per_step'] == 4 and v['h2d_bytes_per_step'] == 26 * 65536 * 8
+  assert d['e2e']['value'] < v['value'] < d['value']
+  names = {r['kernel'] for r in d['roofline_all']}
+  assert {'lookup_fwd', 'sparse_update', 'sparse_update_long', 'sort_pass'} <= names
+  n8 = json.load(open(os.path.join(ROOT, 'profiles', 'bench_r2_n8.json')))
+  assert n8['n_gpus'] == 8 and n8['extra']['owner_load_unique_rows']['max_over_mean'] < 1.1
+  assert n8['extra']['dedup']['wire_reduction'] > 3
