@@ -138,7 +138,7 @@ SYMBOLS = [
     'hbAlltoallvNSizes', 'hbAlltoallvN',
     'hbShardedPlanCreate', 'hbShardedPlanDestroy', 'hbShardedPlanWindowBytes',
     'hbShardedLookupForward', 'hbShardedLookupBackwardUpdate',
-    'hbGroupLookupForwardHost',
+    'hbGroupLookupForwardHost', 'hbH2DTransferN',
 ]
 
 _lib = None

@@ -11,3 +11,4 @@ from hybridbackend_b200.embedding.cache import lookup
 from hybridbackend_b200.embedding.checkpoint import merge_shards
 from hybridbackend_b200.embedding.checkpoint import logical_rows_of_merged
 from hybridbackend_b200.embedding.checkpoint import split_merged
+from hybridbackend_b200.embedding.transfer import h2d_transfer_n

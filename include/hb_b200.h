@@ -354,6 +354,17 @@ int hbGroupLookupForwardHost(int n, const hbLookupFeature* feats,
                              void* h_out_block, size_t out_block_bytes,
                              int32_t* d_status, hbStream stream);
 
+/* ---------------------------------------------------------------------------
+ * Fused multi-tensor host -> device staging of the step's sparse features.
+ * Replaces HbH2DTransferN (ops/transfer/transfer.cc:68-80, transfer_functors.cu.cc:38-238):
+ * n host tensors of bytes[k] bytes reach n device tensors.  Inputs in pinned (page-locked)
+ * host memory are read by ONE kernel launch straight over PCIe (zero copy, 128-bit
+ * loads); pageable inputs fall back to one cudaMemcpyAsync each, as in the reference.
+ * Everything is enqueued on `stream`; nothing is synchronised.
+ * ------------------------------------------------------------------------- */
+int hbH2DTransferN(int n, const void* const* h_inputs, void* const* d_outputs,
+                   const int64_t* bytes, hbStream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,3 +93,29 @@ def test_unique_id_bootstrap_world1(hb):
   coll.close()
   with pytest.raises(RuntimeError):
     hb.distribute.Collective(0, 1, window_bytes=1 << 20, unique_id=bytes(128))
+
+
+def test_h2d_transfer_n(hb):
+  """HbH2DTransferN: pinned inputs in one zero-copy kernel, pageable ones by copy; odd
+  sizes, empty tensors and mixed dtypes (ids int64, offsets int64, dense float32)."""
+  g = torch.Generator().manual_seed(3)
+  shapes = [(65536,), (0,), (4097,), (13,), (1,), (300, 7)]
+  host = []
+  for i, s in enumerate(shapes):
+    t = torch.randint(-2**40, 2**40, s, dtype=torch.int64, generator=g) if i % 2 == 0 else torch.randn(s, generator=g)
+    host.append(t.pin_memory() if i != 3 else t)   # one pageable tensor
+  host.append(torch.arange(1000, dtype=torch.int32).pin_memory()[3:])   # unaligned view (offset 12 B)
+  l0 = hb._lib.lib().hbGetLaunchCount()
+  out = hb.embedding.h2d_transfer_n(host)
+  torch.cuda.synchronize()
+  assert hb._lib.lib().hbGetLaunchCount() - l0 == 1   # one kernel for all pinned tensors
+  for h, d in zip(host, out):
+    assert d.is_cuda and d.dtype == h.dtype and tuple(d.shape) == tuple(h.shape)
+    assert torch.equal(d.cpu(), h)
+  # reuse of caller-provided outputs, then straight into a lookup
+  ids = torch.randint(0, 1000, (512,), dtype=torch.int64).pin_memory()
+  d_ids = torch.empty(512, dtype=torch.int64, device='cuda')
+  hb.embedding.h2d_transfer_n([ids], [d_ids])
+  table = torch.randn(1000, 16, device='cuda')
+  got = hb.embedding.embedding_lookup(table, d_ids, check=True)
+  assert torch.equal(got.cpu(), table.cpu()[ids])
