@@ -1,10 +1,9 @@
 // bucket.cuh -- stable multi-segment bucket scatter for sm_100a.
 //
-// One mechanism serves two users:
-//   * K1 partition (HbPartitionByModulo[N] / dual modulo): bin = shard(id),
-//     emits permuted ids, per-bin sizes and the inverse permutation;
-//   * the LSD radix sort that groups row ids before the fused sparse update
-//     (bin = 9-bit digit, carries the bag index as value).
+// K1 partition (HbPartitionByModulo[N] / dual modulo): bin = shard(id), emits the
+// permuted ids, per-bin sizes and the inverse permutation.  (Round 1 also ran the
+// backward's LSD radix sort through this mechanism, one launch per digit; that job
+// moved to the one-launch cluster kernel of cluster_sort.cuh.)
 // Launches (ALL segments = features at once):
 //   memset  : zero histograms, tile status words and tickets (one node)
 //   hist    : global per-(segment, pass, bin) histograms of EVERY digit position in
@@ -109,68 +108,6 @@ struct DualModuloTraits {  // partition_by_dual_modulo_functors.cc:37-49,:66-71
   static __device__ __forceinline__ int bin(In v, const BucketParams& P, const BucketSeg&, int) {
     const int pre = floor_mod<T>(v, P.p * P.m);
     return STAGE == 1 ? pre % P.p : pre / P.m;
-  }
-};
-
-struct RadixFirstTraits {  // int64 global id -> uint32 local row, first digit
-  using In = int64_t;
-  using Out = uint32_t;
-  static constexpr bool kRadix = true;
-  static __device__ __forceinline__ Out conv(In v, const BucketParams& P, const BucketSeg& sg) {
-    if (v == INT64_MIN) return 0xFFFFFFFFu;  // padding entry: skipped silently
-    if (v < 0) return 0xFFFFFFFEu;           // invalid id: skipped, raises the status word
-    const uint64_t r = (P.div_shift >= 0) ? ((uint64_t)v >> P.div_shift) : (uint64_t)(v / P.div);
-    return (r >= (uint64_t)sg.key_limit) ? 0xFFFFFFFEu : (uint32_t)r;
-  }
-  static __device__ __forceinline__ int bin(In v, const BucketParams& P, const BucketSeg& sg, int shift) {
-    return (int)((conv(v, P, sg) >> shift) & (uint32_t)(P.nbins - 1));
-  }
-};
-
-// int64 global id -> (owner << lbits) | local row: the requester-side sort of the
-// sharded path groups the ids by owner rank first and by row inside an owner
-// (owner = id % W, local row = id / W, embedding/sharding.py:182-189), so unique
-// ids come out already partitioned.  P.p = W.
-struct RadixCompositeTraits {
-  using In = int64_t;
-  using Out = uint32_t;
-  static constexpr bool kRadix = true;
-  static __device__ __forceinline__ Out conv(In v, const BucketParams& P, const BucketSeg& sg) {
-    if (v == INT64_MIN) return 0xFFFFFFFFu;
-    if (v < 0) return 0xFFFFFFFEu;
-    uint64_t own, r;
-    if (P.div_shift >= 0) { own = (uint64_t)v & (uint64_t)(P.p - 1); r = (uint64_t)v >> P.div_shift; }
-    else { own = (uint64_t)v % (uint64_t)P.p; r = (uint64_t)v / (uint64_t)P.p; }
-    if (r >= (uint64_t)sg.key_limit) return 0xFFFFFFFEu;
-    return (uint32_t)((own << sg.lbits) | r);
-  }
-  static __device__ __forceinline__ int bin(In v, const BucketParams& P, const BucketSeg& sg, int shift) {
-    return (int)((conv(v, P, sg) >> shift) & (uint32_t)(P.nbins - 1));
-  }
-};
-
-// uint32 keys given directly (owner side of the sharded path: local rows received
-// from the requesters); keys >= key_limit are invalid.
-struct RadixDirectTraits {
-  using In = uint32_t;
-  using Out = uint32_t;
-  static constexpr bool kRadix = true;
-  static __device__ __forceinline__ Out conv(In v, const BucketParams&, const BucketSeg& sg) {
-    if (v == 0xFFFFFFFFu) return v;
-    return v >= sg.key_limit ? 0xFFFFFFFEu : v;
-  }
-  static __device__ __forceinline__ int bin(In v, const BucketParams& P, const BucketSeg& sg, int shift) {
-    return (int)((conv(v, P, sg) >> shift) & (uint32_t)(P.nbins - 1));
-  }
-};
-
-struct RadixNextTraits {
-  using In = uint32_t;
-  using Out = uint32_t;
-  static constexpr bool kRadix = true;
-  static __device__ __forceinline__ Out conv(In v, const BucketParams&, const BucketSeg&) { return v; }
-  static __device__ __forceinline__ int bin(In v, const BucketParams& P, const BucketSeg&, int shift) {
-    return (int)((v >> shift) & (uint32_t)(P.nbins - 1));
   }
 };
 

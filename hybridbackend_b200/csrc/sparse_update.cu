@@ -262,10 +262,15 @@ __device__ __forceinline__ int seg_find(const int* s_begin, int nsegs, int unit)
 //                  idling).
 //   long kernel  : one warp per queued piece, kLongRows x 128-bit loads per lane in flight.
 constexpr int kPieceBytes = 16384;   // gradient bytes per hot-row piece
-constexpr int kMaxPiece = 128;       // entries per piece at most
+constexpr int kMaxPiece = 512;       // entries per piece at most
 
 static inline int piece_rows(int dim) {
-  int p = kPieceBytes / (dim * 4);
+  static const int piece_bytes = [] {   // HB_PIECE_BYTES: tuning knob (power of two, 2 KB .. 64 KB)
+    const char* e = getenv("HB_PIECE_BYTES");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 2048 && v <= 65536 && (v & (v - 1)) == 0) ? v : kPieceBytes;
+  }();
+  int p = piece_bytes / (dim * 4);
   if (p > kMaxPiece) p = kMaxPiece;
   if (p < 8) p = 8;
   return p;
@@ -684,8 +689,7 @@ static void upd_shape(int dim, int* log2g, int* v) {
   *v = p;
 }
 
-constexpr int kRadixBits = 9;
-constexpr int kRadixBins = 1 << kRadixBits;
+constexpr int kRadixBits = kCsBits;   // digit width of the cluster sort
 
 // per-feature workspace layout (a function of nnz, dim and offsets != NULL only)
 struct UpdLayout {
