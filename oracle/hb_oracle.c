@@ -171,7 +171,9 @@ int hbo_is_small_table(int64_t bucket_size, int num_shards, int64_t batch_size) 
 }
 
 /* ------------------------------------------------------------------------- */
-/* tf.unique (TF-1.15 UniqueOp, CPU): first-occurrence order, int32 inverse.  */
+/* tf.unique (TF-1.15 UniqueOp, CPU: tensorflow/core/kernels/unique_op.cc,    */
+/* UniqueOp::Compute -- hash map in input order): first-occurrence order,     */
+/* int32 inverse.                                                            */
 /* ------------------------------------------------------------------------- */
 typedef struct {
   int64_t* keys;
@@ -229,6 +231,13 @@ int64_t hbo_unique_i64(const int64_t* ids, int64_t n, int64_t* uniq,
 /*   out = sparse_segment_{sum,mean,sqrtn}(emb, idx, segment_ids)             */
 /* The segment reduction accumulates rows in index order in fp32; mean        */
 /* divides the sum by the count, sqrtn by sqrt(count).  PARITY UNPINNED.      */
+/* TF-1.15 sources restated (tensorflow==1.15.5, not under /root/reference):  */
+/*   python/ops/embedding_ops.py  embedding_lookup_sparse (:unique, :gather,  */
+/*     sparse_segment_* with sp_weights None)                                 */
+/*   core/kernels/segment_reduction_ops.cc  SparseSegmentReductionOpBase::    */
+/*     Compute -- CPU: one output row at a time, inputs added in index order  */
+/*     (Reduce() over 1..8 rows at a time, left to right), then the mean /    */
+/*     sqrtn scale by 1/N resp. 1/sqrt(N) applied as a DIVISION of the sum    */
 /* ------------------------------------------------------------------------- */
 static inline void finish_bag(float* o, int dim, int64_t cnt, int combiner) {
   if (cnt == 0) return;
@@ -287,8 +296,9 @@ int hbo_embedding_bag(const float* table, int64_t rows, int dim,
 }
 
 /* Gradient of sparse_segment_{sum,mean,sqrtn} w.r.t. the gathered rows
- * (TF math_grad.py _SparseSegment*Grad): row p receives grad[bag(p)], divided
- * by count (mean) or sqrt(count) (sqrtn).  PARITY UNPINNED. */
+ * (TF python/ops/math_grad.py _SparseSegment{Sum,Mean,SqrtN}Grad ->
+ * core/kernels/segment_reduction_ops.cc SparseSegmentGradOpBase): row p receives
+ * grad[bag(p)], divided by count (mean) or sqrt(count) (sqrtn).  PARITY UNPINNED. */
 int hbo_lookup_row_grads(const float* grad, int64_t grad_stride, int dim,
                          const int64_t* offsets, int64_t nbags, int combiner,
                          float* row_grad) {
@@ -306,9 +316,12 @@ int hbo_lookup_row_grads(const float* grad, int64_t grad_stride, int dim,
   return 0;
 }
 
-/* optimizer.py _apply_sparse_duplicate_indices -> _deduplicate_indexed_slices:
- * unique + unsorted_segment_sum (position order), then one apply per unique
- * row.  Returns summed grads in sum_g [u, dim] and unique rows; caller frees. */
+/* python/training/optimizer.py _apply_sparse_duplicate_indices ->
+ * _deduplicate_indexed_slices: unique + unsorted_segment_sum, then one apply per
+ * unique row.  CPU UnsortedSegmentSum (core/kernels/segment_reduction_ops.cc,
+ * UnsortedSegmentFunctor<CPUDevice>) walks the input rows 0..N-1 once and adds row i
+ * into output[segment_ids[i]]: per unique row the additions happen in POSITION order,
+ * which is the order restated here (and the order the GPU kernels bound against).  Returns summed grads in sum_g [u, dim] and unique rows; caller frees. */
 static int64_t dedup_sum(const int64_t* rows_idx, const float* row_grad,
                          int64_t nnz, int dim, int64_t** uniq_out,
                          float** sum_out) {
@@ -329,7 +342,11 @@ static int64_t dedup_sum(const int64_t* rows_idx, const float* row_grad,
   return u;
 }
 
-/* TF-1.15 training_ops.cc SparseApplyAdagrad (update_slots=true, no epsilon):
+/* TF-1.15 core/kernels/training_ops.cc SparseApplyAdagradOp<CPUDevice>::Compute
+ * (update_slots=true, no epsilon).  The published semantics are restated with IEEE sqrt
+ * and divide; TF's vectorised inner loop may evaluate the same expression as a multiply
+ * by an (Eigen) rsqrt, whose last-bit behaviour is not reproducible without the binary --
+ * one of the reasons this function is labelled PARITY UNPINNED:
  *   accum[r] += g*g ; var[r] -= lr * g / sqrt(accum[r]).  PARITY UNPINNED. */
 int hbo_sparse_apply_adagrad(float* table, float* accum, int64_t rows, int dim,
                              const int64_t* rows_idx, const float* row_grad,
@@ -352,7 +369,9 @@ int hbo_sparse_apply_adagrad(float* table, float* accum, int64_t rows, int dim,
   return 0;
 }
 
-/* tf.contrib.opt.LazyAdamOptimizer._apply_sparse (TF-1.15):
+/* tf.contrib.opt.LazyAdamOptimizer._apply_sparse (TF-1.15:
+ * tensorflow/contrib/opt/python/training/lazy_adam_optimizer.py -- gather m, v of the
+ * touched rows, update, scatter_update back):
  *   lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)
  *   m[r] = b1*m[r] + (1-b1)*g ; v[r] = b2*v[r] + (1-b2)*g*g
  *   var[r] -= lr_t * m[r] / (sqrt(v[r]) + eps)          PARITY UNPINNED. */
