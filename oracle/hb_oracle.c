@@ -234,10 +234,12 @@ int64_t hbo_unique_i64(const int64_t* ids, int64_t n, int64_t* uniq,
 /* TF-1.15 sources restated (tensorflow==1.15.5, not under /root/reference):  */
 /*   python/ops/embedding_ops.py  embedding_lookup_sparse (:unique, :gather,  */
 /*     sparse_segment_* with sp_weights None)                                 */
-/*   core/kernels/segment_reduction_ops.cc  SparseSegmentReductionOpBase::    */
-/*     Compute -- CPU: one output row at a time, inputs added in index order  */
-/*     (Reduce() over 1..8 rows at a time, left to right), then the mean /    */
-/*     sqrtn scale by 1/N resp. 1/sqrt(N) applied as a DIVISION of the sum    */
+/*   core/kernels/segment_reduction_ops.cc  SparseSegmentReductionOpBase (CPU) */
+/*     -- one output row at a time, input rows taken in index order.  How the   */
+/*     kernel groups the additions and where it applies the mean / sqrtn scale */
+/*     for long bags cannot be checked without the TF sources or binary; the   */
+/*     restatement is the sequential sum followed by one division (exact for   */
+/*     the bag lengths 1..2, the published semantics beyond)                   */
 /* ------------------------------------------------------------------------- */
 static inline void finish_bag(float* o, int dim, int64_t cnt, int combiner) {
   if (cnt == 0) return;
