@@ -138,3 +138,43 @@ def test_checkpoint_layout_roundtrip(hb):
     logical = torch.empty_like(merged)
     logical[perm] = merged
     assert torch.equal(logical, table)
+
+
+def test_bench_id_scramble_spreads_the_hot_rows_over_the_owners():
+  """bench.gen_ids_numpy: with the per-feature salt the hottest id of each feature maps to a
+  different row, so under id % W sharding no rank owns the hot row of every table (the
+  round-1 scramble sent rank 1 of EVERY table to id 0 -> owner 0)."""
+  import collections
+  import bench
+  W = 8
+  owners = collections.Counter()
+  for k, vocab in enumerate(bench.CRITEO_SIZES):
+    if vocab <= W:
+      continue
+    ids = bench.gen_ids_numpy(np.random.RandomState(k), 20000, vocab, 'zipf', 1.05, salt=k)
+    assert ids.min() >= 0 and ids.max() < vocab
+    vals, cnt = np.unique(ids, return_counts=True)
+    owners[int(vals[np.argmax(cnt)]) % W] += 1
+  assert len(owners) >= 5 and max(owners.values()) <= 8, owners
+  # salt 0 reproduces the unsalted stream (old fixtures stay valid)
+  a = bench.gen_ids_numpy(np.random.RandomState(1), 1000, 12345, 'zipf', 1.05)
+  b = bench.gen_ids_numpy(np.random.RandomState(1), 1000, 12345, 'zipf', 1.05, salt=0)
+  assert np.array_equal(a, b)
+
+
+def test_group_window_bytes_covers_plan_and_replicated_allreduce():
+  """The Collective window a GroupLookup needs = sharded plan + both halves of the dense
+  all-reduce of the replicated small tables (hbAllreduceSumF32: world x count floats each)."""
+  from hybridbackend_b200.embedding.sharded import group_window_bytes, plan_window_bytes
+  import bench
+  W, B, D = 8, 65536, 64
+  sizes = bench.CRITEO_SIZES
+  sh = [n for n in sizes if n > W]
+  plan = plan_window_bytes(W, [B] * len(sh), [D] * len(sh), W)
+  total = group_window_bytes(W, sizes, [D] * len(sizes), [B] * len(sizes), W)
+  dense_floats = sum(n * D for n in sizes if n <= W)
+  assert dense_floats == 7 * D                       # the 3- and 4-row Criteo tables
+  assert total >= plan + 2 * W * dense_floats * 4    # what failed at N=8 before the helper existed
+  assert total - plan < (4 << 20)
+  # one rank: nothing is sharded, nothing is all-reduced
+  assert group_window_bytes(1, sizes, [D] * len(sizes), [B] * len(sizes)) <= (2 << 20)
