@@ -143,6 +143,14 @@ def test_adagrad_run_lengths_around_the_kernel_thresholds(hb, oracle):
   _run_bounded(hb, oracle, [200000], 256, 12000, gen, steps=1)
 
 
+def test_adagrad_more_than_eight_tiles_per_feature(hb, oracle):
+  """150 000 ids in ONE feature = 19 tiles of the cluster sort: every CTA of the cluster
+  owns 2-3 tiles and re-ranks them in the scatter phase (the one-tile-per-CTA fast path
+  keeps ranks in registers); 3 digit passes (500 k rows) and 1 pass (300 rows)."""
+  _run_bounded(hb, oracle, [500000, 300], 16, 150000,
+               lambda rng, B, r: (rng.zipf(1.2, B) % r).astype(np.int64), steps=1)
+
+
 def test_adagrad_fast_math_within_bound(hb, oracle):
   """HB_OPT_FLAG_FAST_MATH (sqrt.approx / div.approx, the arithmetic class of TF's
   GPU kernels): within 1e-5 relative of the IEEE result, and inside the run-length
