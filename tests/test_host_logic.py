@@ -178,3 +178,35 @@ def test_group_window_bytes_covers_plan_and_replicated_allreduce():
   assert total - plan < (4 << 20)
   # one rank: nothing is sharded, nothing is all-reduced
   assert group_window_bytes(1, sizes, [D] * len(sizes), [B] * len(sizes)) <= (2 << 20)
+
+
+def test_checkpoint_save_merge_restore_protocol(tmp_path):
+  """training/saver.py:89-180 in a neutral container: every rank saves `<name>/part_<rank>`
+  (+ slots) with its SaveSliceInfo, the chief merges, each rank restores its slice; the
+  merged variable has the reference's layout (shard s at rows [shard_offset(s), +rows(s)),
+  holding logical ids r * W + s)."""
+  from hybridbackend_b200.embedding import checkpoint as ck
+  from hybridbackend_b200.embedding.sharding import shard_rows
+  W, n, D = 3, 100, 4
+  logical = torch.arange(n * D, dtype=torch.float32).reshape(n, D)      # row g = embedding of id g
+  acc = logical * 0.5
+  prefix = str(tmp_path / 'model.ckpt-7')
+  for r in range(W):
+    part, apart = logical[r::W].contiguous(), acc[r::W].contiguous()
+    assert part.shape[0] == shard_rows(n, W, r)
+    p = ck.save_local_shards(prefix, 'abc123', r, W, {'emb': (n, part)}, {'emb': {'Adagrad': apart}})
+    assert p.endswith(f'part-{r:05d}.npz')
+  out = ck.merge_checkpoint(prefix, 'abc123', W)
+  assert out == prefix + '.npz' and not (tmp_path / 'model.ckpt-7_temp_abc123').exists()
+  with np.load(out) as z:
+    merged = torch.from_numpy(z['emb'])
+  assert torch.equal(merged, ck.merge_shards([logical[r::W] for r in range(W)], n))
+  perm = ck.logical_rows_of_merged(n, W)
+  assert torch.equal(merged, logical[perm])            # merged row m holds logical id perm[m]
+  for r in range(W):
+    got = ck.restore_local_shards(prefix, r, W)
+    assert torch.equal(got['emb'], logical[r::W]) and torch.equal(got['emb/Adagrad'], acc[r::W])
+  with pytest.raises(ValueError):
+    ck.restore_local_shards(prefix, 0, W + 1)
+  with pytest.raises(FileNotFoundError):
+    ck.merge_checkpoint(prefix, 'missing', W)
