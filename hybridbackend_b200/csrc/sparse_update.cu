@@ -768,14 +768,9 @@ template <int V, int OPT, int MODE, bool FAST>
 static int launch_apply(const UpdParams& U, int which, cudaStream_t stream) {
   int per_sm = 0;
   if (which == 0) {
-    if constexpr (V == 1) {
-      static const int occ = [] { const char* e = getenv("HB_SHORT_OCC"); return e ? atoi(e) : 4; }();
-      if (occ == 4) return launch_short<V, OPT, MODE, FAST, 4>(U, stream);
-      if (occ == 6) return launch_short<V, OPT, MODE, FAST, 6>(U, stream);
-      return launch_short<V, OPT, MODE, FAST, 5>(U, stream);
-    } else {
-      return launch_short<V, OPT, MODE, FAST, (V == 2 ? 3 : 1)>(U, stream);
-    }
+    // CTAs per SM: measured at V = 1 (D <= 128) -- 4 (64 regs, no spills) 82 us, 5 (48 regs)
+    // 91 us, 6 (40 regs) 98 us on the C2 workload: spills cost more than occupancy gains
+    return launch_short<V, OPT, MODE, FAST, (V == 1 ? 4 : (V == 2 ? 3 : 1))>(U, stream);
   } else {
     HB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
         &per_sm, update_long_kernel<V, OPT, MODE, FAST>, kUpdThreads, 0));
