@@ -3,8 +3,9 @@
  *
  * Every entry point is `extern "C"`, takes plain pointers / sizes / a CUDA stream
  * (passed as void* so the header needs no CUDA include), enqueues work on that
- * stream and returns an int status (HB_OK = 0).  No entry point allocates an
- * output, synchronises the device, or throws; scratch comes from caller-provided
+ * stream and returns an int status (HB_OK = 0).  No per-step entry point allocates an
+ * output, synchronises the device, or throws (the Create / Destroy / Connect calls of
+ * communicators and plans do allocate and synchronise: setup time); scratch comes from caller-provided
  * workspaces sized by the matching *WorkspaceBytes query (the TF shim uses
  * allocate_temp, the Python harness torch.empty).  Host arrays of device pointers
  * are read before the call returns.  Callable from any thread.
@@ -293,13 +294,17 @@ int hbAllreduceSumF32(hbComm* comm, const float* d_in, float* d_out, int64_t cou
 /* ---------------------------------------------------------------------------
  * K1+K2+K3+K4 fused: sharded GroupLookup (additive op; its oracle is the
  *   composition embedding/sharding.py:171-203 of the ops above).
- * Forward, per rank:  partition ids by id % W -> push bucketed ids + sizes to
- * owners -> owners gather rows (local row = id / W) and store them straight
- * into the requester's window in its partitioned order -> requester stitches and
- * pools into out.  Zero host synchronisation, static shapes.
- * Backward: requester pushes per-id row gradients to owners; owners sum
- * duplicates deterministically and apply the optimizer (sharded gradients are
- * not averaged: training/gradient.py:216-217).
+ * Forward, per rank: sort the ids by (owner = id % W, local row = id / W) and
+ * deduplicate them -> push the UNIQUE local rows (32 bit) + counts to their owners
+ * -> owners gather the rows and store them straight into the requester's window at
+ * the slot of the unique -> requester expands through the inverse map while it
+ * pools into out.  Zero host synchronisation, static shapes; only unique ids, rows
+ * and gradient sums cross NVLink.  The owner's sort of the received rows (needed by
+ * the backward) is enqueued at forward time on a plan-owned side stream.
+ * Backward: requester sums the row gradients of each unique id (position order)
+ * straight into the owner's window; owners sum the per-rank contributions of a row
+ * in rank order and apply the optimizer (sharded gradients are not averaged:
+ * training/gradient.py:216-217).
  * ------------------------------------------------------------------------- */
 typedef struct hbShardedFeature {
   float* shard;           /* local shard [shard_rows, dim] */
@@ -323,8 +328,10 @@ typedef struct hbShardedPlan hbShardedPlan;
  * capacity_factor >= 1: owner-side receive capacity per feature =
  * ceil(capacity_factor * max_nnz[k]) ids (W*max_nnz is always safe; receive counts
  * stay on the device, so capacity costs memory, not work).  Overflow raises
- * HB_STATUS_WINDOW_OVERFLOW.  Limits: n <= 64 features per plan, all dims <= 128
- * (or all in the same 128-wide class); one plan per communicator.  Every rank
+ * HB_STATUS_WINDOW_OVERFLOW on EVERY rank.  Limits: n <= 256 features per plan, dims
+ * multiples of 4 up to 1024, one plan per communicator at a time (PlanDestroy frees the
+ * slot; epochs are monotonic across plans).  PlanCreate / PlanDestroy allocate and
+ * synchronise the device (setup time, not per step).  Every rank
  * must issue the same Forward / BackwardUpdate sequence; a peer that never
  * arrives raises HB_STATUS_PEER_TIMEOUT after 20 s instead of hanging. */
 int hbShardedPlanCreate(hbComm* comm, int n, const int64_t* max_nnz,
